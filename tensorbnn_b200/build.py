@@ -1,0 +1,64 @@
+"""Builds tensorbnn_b200/libtbnn.so (CUDA, sm_100a) in-tree with nvcc.
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libtbnn.so")
+SOURCES = ["api.cu", "k_main.cu", "k_hyper.cu", "k_predict.cu", "k_adapter.cu", "k_persist.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    nvcc = _nvcc()
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "tbnn.h"))
+    objs = []
+    logs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        if not os.path.exists(s):
+            continue
+        o = os.path.join(CSRC, src[:-3] + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            logs.append(r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed on " + src)
+            if verbose:
+                sys.stderr.write(r.stderr)
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB, "\n".join(logs)
+
+
+if __name__ == "__main__":
+    lib, log = build_library(force="--force" in sys.argv, verbose=True)
+    print(lib)

@@ -1,0 +1,387 @@
+// k_main.cu -- main-chain kernels: padded layout conversion, per-CTA likelihood partial
+// gradients (the row sweep), gradient assembly + priors + leapfrog update, momentum draw,
+// Metropolis-Hastings select.  Reference call sites: network.py:370-392 (target),
+// :394-411 (HMC transition); TFP leapfrog / MH semantics per SURVEY.md Appendix B.
+#include "engine.cuh"
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace tbnn {
+
+// ------------------------------------------------------------------ element decode
+struct Elem { int kind; int blk; int flat; int first; };  // kind: 0 pad, 1 W, 2 b, 3 slope
+__device__ __forceinline__ Elem decode_elem(const ModelPlan& mp, int i) {
+  Elem e; e.kind = 0; e.blk = 0; e.flat = 0; e.first = 0;
+  for (int l = 0; l < mp.nb; ++l) {
+    const BlockPlan& b = mp.b[l];
+    if (i < b.pb) {
+      const int j = i - b.pw, o = j / b.ld_in, k = j - o * b.ld_in;
+      e.blk = l;
+      if (o < b.out && k < b.in) { e.kind = 1; e.flat = b.fw + o * b.in + k; e.first = (j == 0); }
+      return e;
+    }
+    if (i < b.pb + b.out_p) {
+      const int o = i - b.pb;
+      e.blk = l;
+      if (o < b.out) { e.kind = 2; e.flat = b.fb + o; e.first = (o == 0); }
+      return e;
+    }
+    if (b.ps >= 0 && i < b.ps + b.out_p) {
+      const int o = i - b.ps;
+      e.blk = l;
+      if (o < b.out) { e.kind = 3; e.flat = b.fs + o; e.first = (o == 0); }
+      return e;
+    }
+  }
+  return e;
+}
+
+template <typename T>
+__global__ void k_pad(const __grid_constant__ ModelPlan mp, const T* __restrict__ flat,
+                      T* __restrict__ padded) {
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mp.Ppad) return;
+  const Elem e = decode_elem(mp, i);
+  padded[(size_t)c * mp.Ppad + i] = e.kind ? flat[(size_t)c * mp.P + e.flat] : T(0);
+}
+template <typename T>
+__global__ void k_unpad(const __grid_constant__ ModelPlan mp, const T* __restrict__ padded,
+                        T* __restrict__ flat) {
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mp.Ppad) return;
+  const Elem e = decode_elem(mp, i);
+  if (e.kind) flat[(size_t)c * mp.P + e.flat] = padded[(size_t)c * mp.Ppad + i];
+}
+
+// ------------------------------------------------------------------ row sweep
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(NT, 1)
+k_partial(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ theta_pad,
+          const T* __restrict__ X, const T* __restrict__ Y, long long N, T* __restrict__ partial,
+          double* __restrict__ stat_part) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  T* sm = reinterpret_cast<T*>(smraw);
+  const int c = blockIdx.y, s = blockIdx.x;
+  const T* thg = theta_pad + (size_t)c * mp.Ppad;
+  TileCtx<T> cx;
+  cx.sm = sm;
+  cx.G = sm + mp.offG;
+  if (mp.offW >= 0) {
+    T* Ws = sm + mp.offW;
+    for (int i = 4 * threadIdx.x; i < mp.Ppad; i += 4 * blockDim.x) {
+      T v[4];
+      ld4(thg + i, v);
+      st4(Ws + i, v);
+    }
+    cx.Wp = Ws;
+  } else {
+    cx.Wp = thg;
+  }
+  if (BWD)
+    for (int i = threadIdx.x; i < mp.Ppad; i += blockDim.x) cx.G[i] = T(0);
+  __syncthreads();
+  const int TR = mp.TR;
+  const long long ntile = (N + TR - 1) / TR;
+  const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
+  T stat = T(0);
+  for (long long t = t0; t < t1; ++t) {
+    const long long row0 = t * TR;
+    const int nr = (int)((N - row0) < TR ? (N - row0) : TR);
+    load_x_tile<T>(mp, sm + mp.offX, X, row0, nr);
+    wait_x_tile();
+    __syncthreads();
+    if (BWD) {
+      stat += tile_forward_backward<T>(mp, cx, Y, row0, nr);
+    } else {
+      tile_forward<T>(mp, cx);
+      stat += lik_phase<T>(mp, cx, Y, row0, nr, sm + mp.offDa);
+    }
+  }
+  if (BWD) {
+    T* out = partial + ((size_t)c * S + s) * mp.Ppad;
+    for (int i = 4 * threadIdx.x; i < mp.Ppad; i += 4 * blockDim.x) {
+      T v[4];
+      ld4(cx.G + i, v);
+      st4(out + i, v);
+    }
+  }
+  double* red = reinterpret_cast<double*>(sm + mp.offRed);
+  const double tot = block_sum((double)stat, red);
+  if (threadIdx.x == 0) stat_part[(size_t)c * S + s] = tot;
+}
+
+// Local reduction before an all-reduce (row-sharded sampling).
+template <typename T>
+__global__ void k_reduce_partials(const __grid_constant__ ModelPlan mp, int S,
+                                  const T* __restrict__ partial, const double* __restrict__ stat_part,
+                                  T* __restrict__ gsum) {
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = mp.Ppad + 4;
+  if (i < mp.Ppad) {
+    double g = 0.0;
+    for (int s = 0; s < S; ++s) g += (double)partial[((size_t)c * S + s) * mp.Ppad + i];
+    gsum[(size_t)c * W + i] = (T)g;
+  } else if (i == mp.Ppad) {
+    double st = 0.0;
+    for (int s = 0; s < S; ++s) st += stat_part[(size_t)c * S + s];
+    gsum[(size_t)c * W + i] = (T)st;
+  }
+}
+
+// ------------------------------------------------------------------ priors
+// value and d/dtheta of one element's prior term (layer.py:177-195, :357-375;
+// activationFunctions.py:189-190, :341-346 with the passed hyper slice, Q4).
+template <typename T>
+__device__ __forceinline__ void prior_elem(const ModelPlan& mp, const Elem& e, const T* hy, double x,
+                                           double& val, double& grad) {
+  const BlockPlan& b = mp.b[e.blk];
+  const double kLog2Pi = 1.8378770664093453;
+  if (e.kind == 3) {
+    if (b.act == ACT_SQPRELU) {
+      const double mean = (double)hy[b.ha];
+      double sd = (double)hy[b.ha + 1];
+      sd = fmin(fmax(sd, 1e-8), 1e8);
+      const double d = (x - mean) / sd;
+      val = -0.5 * d * d;
+      grad = -d / sd;
+      if (e.first) val += -0.5 * (2.0 * log(sd) + kLog2Pi);
+    } else {  // ACT_PRELU: exponentialLogProb(rate, slopes)
+      const double r = fabs((double)hy[b.ha]);
+      val = -r * x + log(r);
+      grad = -r;
+    }
+    return;
+  }
+  const int h0 = b.hw + (e.kind == 1 ? 0 : 2);
+  const double loc = (double)hy[h0];
+  const double sc = (double)hy[h0 + 1] * (double)hy[h0 + 1];
+  if (b.prior == PRIOR_CAUCHY) {   // +log(1+z^2) - log(pi*gamma)   (BNN_functions.py:51-56, Q1)
+    const double z = (x - loc) / sc;
+    val = log1p(z * z) - log(3.14159265358979323846 * sc);
+    grad = 2.0 * z / ((1.0 + z * z) * sc);
+  } else {                          // multivariateLogProb with scalar sigma (BNN_functions.py:21-32, Q2)
+    const double sg = fmin(fmax(sc, 1e-8), 1e8);
+    const double d = (x - loc) / sg;
+    val = -0.5 * d * d;
+    grad = -d / sg;
+    if (e.first) val += -0.5 * (2.0 * log(sg) + kLog2Pi);
+  }
+}
+
+// ------------------------------------------------------------------ gradient assembly + update
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_finalize(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ partial,
+           const double* __restrict__ stat_part, const T* __restrict__ gsum,
+           const T* __restrict__ hyper, long long Ntot, T* __restrict__ theta_pad,
+           T* __restrict__ mom_pad, T* __restrict__ grad_pad, const T* __restrict__ eps_dev,
+           StepCoef cf, double* __restrict__ logp, double* __restrict__ stat_out,
+           double* __restrict__ prior_part, unsigned* __restrict__ ticket) {
+  __shared__ double red[40];
+  __shared__ int is_last;
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const T* hy = hyper + (size_t)c * mp.H;
+  // likelihood scale 1/sigma^2 (Gaussian kinds)
+  double sg = 1.0, scale = 1.0;
+  if (mp.lik == LIK_GAUSS) {
+    const double h = (double)hy[mp.lik_h];
+    sg = fmin(fmax(h * h, 1e-8), 1e8);
+    scale = 1.0 / (sg * sg);
+  } else if (mp.lik == LIK_FIXED) {
+    sg = fmin(fmax(mp.fixed_sd, 1e-8), 1e8);
+    scale = 1.0 / (sg * sg);
+  }
+  double pv = 0.0;
+  if (i < mp.Ppad) {
+    const Elem e = decode_elem(mp, i);
+    const size_t gi = (size_t)c * mp.Ppad + i;
+    if (e.kind) {
+      double g = 0.0;
+      if (gsum) {
+        g = (double)gsum[(size_t)c * (mp.Ppad + 4) + i];
+      } else {
+        for (int s = 0; s < S; ++s) g += (double)partial[((size_t)c * S + s) * mp.Ppad + i];
+      }
+      const T th = theta_pad[gi];
+      double pg = 0.0;
+      prior_elem<T>(mp, e, hy, (double)th, pv, pg);
+      const T gt = (T)(g * scale + pg);
+      grad_pad[gi] = gt;
+      if (cf.m1 != 0.0 || cf.m2 != 0.0 || cf.m3 != 0.0) {
+        const T eps = eps_dev[c];
+        T p = mom_pad[gi];
+        if (cf.m1 != 0.0) p = p + (T(cf.m1) * eps) * gt;
+        if (cf.m2 != 0.0) p = p - (T(cf.m2) * eps) * gt;
+        mom_pad[gi] = p;
+        if (cf.m3 != 0.0) theta_pad[gi] = th + (T(cf.m3) * eps) * p;
+      }
+    } else {
+      grad_pad[gi] = T(0);
+    }
+  }
+  if (logp == nullptr) return;
+  const double bs = block_sum(pv, red);
+  if (threadIdx.x == 0) {
+    prior_part[(size_t)c * gridDim.x + blockIdx.x] = bs;
+    __threadfence();
+    const unsigned t = atomicAdd(&ticket[c], 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x)
+    acc += __ldcg(&prior_part[(size_t)c * gridDim.x + j]);
+  const double prior = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    double st = 0.0;
+    if (gsum) st = (double)gsum[(size_t)c * (mp.Ppad + 4) + mp.Ppad];
+    else for (int s = 0; s < S; ++s) st += stat_part[(size_t)c * S + s];
+    double ll;
+    if (mp.lik == LIK_BERN) {
+      ll = st;
+    } else {
+      const double n = (double)Ntot * (double)mp.OUT;
+      ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * 1.8378770664093453);
+    }
+    logp[c] = prior + ll;
+    if (stat_out) stat_out[c] = st;
+    ticket[c] = 0u;
+  }
+}
+
+// ------------------------------------------------------------------ momentum draw
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_momentum(const __grid_constant__ ModelPlan mp, uint64_t seed, uint64_t call,
+           const T* __restrict__ injected_flat, T* __restrict__ mom_pad, double* __restrict__ ke) {
+  __shared__ double red[40];
+  const int c = blockIdx.x;
+  double k = 0.0;
+  for (int i = threadIdx.x; i < mp.Ppad; i += blockDim.x) {
+    const Elem e = decode_elem(mp, i);
+    T p = T(0);
+    if (e.kind) {
+      p = injected_flat ? injected_flat[(size_t)c * mp.P + e.flat]
+                        : draw_normal<T>(seed, STREAM_MAIN, call, (uint32_t)c, (uint32_t)e.flat);
+    }
+    mom_pad[(size_t)c * mp.Ppad + i] = p;
+    k += 0.5 * (double)p * (double)p;
+  }
+  k = block_sum(k, red);
+  if (threadIdx.x == 0) ke[c] = k;
+}
+
+// ------------------------------------------------------------------ Metropolis-Hastings
+// log_accept_ratio = safe_sum(logp' - logp + KE0 - KE1); accept iff log u < lar;
+// reported accept prob = where(lar<0, exp(lar), 1)  (network.py:410-411).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_mh(const __grid_constant__ ModelPlan mp, uint64_t seed, uint64_t call, const T* __restrict__ u_in,
+     const T* __restrict__ theta0_pad, const T* __restrict__ theta1_pad,
+     const T* __restrict__ mom1_pad, const double* __restrict__ logp0,
+     const double* __restrict__ logp1, const double* __restrict__ ke0,
+     const double* __restrict__ stat0, const double* __restrict__ stat1,
+     double* __restrict__ stat_cur, T* __restrict__ theta_flat, T* __restrict__ stats) {
+  __shared__ double red[40];
+  __shared__ int acc_s;
+  const int c = blockIdx.x;
+  const size_t base = (size_t)c * mp.Ppad;
+  double k1 = 0.0, sjd = 0.0;
+  for (int i = threadIdx.x; i < mp.Ppad; i += blockDim.x) {
+    const double p = (double)mom1_pad[base + i];
+    const double d = (double)theta1_pad[base + i] - (double)theta0_pad[base + i];
+    k1 += 0.5 * p * p;
+    sjd += d * d;
+  }
+  k1 = block_sum(k1, red);
+  sjd = block_sum(sjd, red);
+  if (threadIdx.x == 0) {
+    const double t[4] = {logp1[c], -logp0[c], ke0[c], -k1};
+    bool nan = false, pinf = false, ninf = false;
+    double lar = 0.0;
+    for (int j = 0; j < 4; ++j) {
+      nan |= isnan(t[j]);
+      pinf |= (isinf(t[j]) && t[j] > 0);
+      ninf |= (isinf(t[j]) && t[j] < 0);
+      lar += t[j];
+    }
+    if (nan || (pinf && ninf)) lar = -INFINITY;
+    const double u = u_in ? (double)u_in[c] : draw_uniform(seed, STREAM_MAIN, call, (uint32_t)c);
+    const int acc = (log(u) < lar) ? 1 : 0;
+    acc_s = acc;
+    if (stats) {
+      stats[c * 4 + 0] = (T)lar;
+      stats[c * 4 + 1] = (T)(lar < 0.0 ? exp(lar) : 1.0);
+      stats[c * 4 + 2] = (T)acc;
+      stats[c * 4 + 3] = (T)(acc ? sjd : 0.0);
+    }
+    if (stat_cur) stat_cur[c] = acc ? stat1[c] : stat0[c];
+  }
+  __syncthreads();
+  const T* src = acc_s ? theta1_pad : theta0_pad;
+  for (int i = threadIdx.x; i < mp.Ppad; i += blockDim.x) {
+    const Elem e = decode_elem(mp, i);
+    if (e.kind) theta_flat[(size_t)c * mp.P + e.flat] = src[base + i];
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+template <typename T>
+void Launch<T>::pad(const ModelPlan& mp, int C, const T* flat, T* padded, cudaStream_t st) {
+  dim3 g((mp.Ppad + 255) / 256, C);
+  k_pad<T><<<g, 256, 0, st>>>(mp, flat, padded);
+}
+template <typename T>
+void Launch<T>::unpad(const ModelPlan& mp, int C, const T* padded, T* flat, cudaStream_t st) {
+  dim3 g((mp.Ppad + 255) / 256, C);
+  k_unpad<T><<<g, 256, 0, st>>>(mp, padded, flat);
+}
+template <typename T>
+void Launch<T>::partial(const ModelPlan& mp, int C, int S, bool backward, const T* theta_pad,
+                        const T* X, const T* Y, long long N, T* partial, double* stat_part,
+                        cudaStream_t st) {
+  dim3 g(S, C);
+  const size_t smem = (size_t)mp.smem_elems * sizeof(T);
+  if (backward) {
+    cudaFuncSetAttribute(k_partial<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_partial<T, true><<<g, NT, smem, st>>>(mp, S, theta_pad, X, Y, N, partial, stat_part);
+  } else {
+    cudaFuncSetAttribute(k_partial<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_partial<T, false><<<g, NT, smem, st>>>(mp, S, theta_pad, X, Y, N, partial, stat_part);
+  }
+}
+template <typename T>
+void Launch<T>::reduce_partials(const ModelPlan& mp, int C, int S, const T* partial,
+                                const double* stat_part, T* gsum, cudaStream_t st) {
+  dim3 g((mp.Ppad + 4 + 255) / 256, C);
+  k_reduce_partials<T><<<g, 256, 0, st>>>(mp, S, partial, stat_part, gsum);
+}
+template <typename T>
+void Launch<T>::finalize(const ModelPlan& mp, int C, int S, const T* partial, const double* stat_part,
+                         const T* gsum, const T* hyper, long long N_total, T* theta_pad, T* mom_pad,
+                         T* grad_pad, const T* eps_dev, StepCoef cf, double* logp, double* stat_out,
+                         double* prior_part, unsigned* ticket, cudaStream_t st) {
+  dim3 g((mp.Ppad + 255) / 256, C);
+  k_finalize<T><<<g, 256, 0, st>>>(mp, S, partial, stat_part, gsum, hyper, N_total, theta_pad, mom_pad,
+                                   grad_pad, eps_dev, cf, logp, stat_out, prior_part, ticket);
+}
+template <typename T>
+void Launch<T>::momentum(const ModelPlan& mp, int C, uint64_t seed, uint64_t call,
+                         const T* injected_flat, T* mom_pad, double* ke, cudaStream_t st) {
+  k_momentum<T><<<C, 256, 0, st>>>(mp, seed, call, injected_flat, mom_pad, ke);
+}
+template <typename T>
+void Launch<T>::mh(const ModelPlan& mp, int C, uint64_t seed, uint64_t call, const T* u_in,
+                   const T* theta0_pad, const T* theta1_pad, const T* mom1_pad, const double* logp0,
+                   const double* logp1, const double* ke0, const double* stat0, const double* stat1,
+                   double* stat_cur, T* theta_flat, T* stats, cudaStream_t st) {
+  k_mh<T><<<C, 256, 0, st>>>(mp, seed, call, u_in, theta0_pad, theta1_pad, mom1_pad, logp0, logp1, ke0,
+                             stat0, stat1, stat_cur, theta_flat, stats);
+}
+
+template struct Launch<float>;
+template struct Launch<double>;
+
+}  // namespace tbnn

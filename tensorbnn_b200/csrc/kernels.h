@@ -1,0 +1,58 @@
+// kernels.h -- host-side launchers of the CUDA kernels (one explicit instantiation per dtype).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plan.h"
+
+namespace tbnn {
+
+// p = a1*eps*g applied as: p += m1*eps*g ; p -= m2*eps*g ; theta += m3*eps*p   (per chain eps)
+struct StepCoef { double m1, m2, m3; };
+
+template <typename T> struct Launch {
+  // flat <-> padded
+  static void pad(const ModelPlan& mp, int C, const T* flat, T* padded, cudaStream_t st);
+  static void unpad(const ModelPlan& mp, int C, const T* padded, T* flat, cudaStream_t st);
+  // likelihood partial gradients: grid (S, C)
+  static void partial(const ModelPlan& mp, int C, int S, bool backward, const T* theta_pad,
+                      const T* X, const T* Y, long long N, T* partial, double* stat_part,
+                      cudaStream_t st);
+  // local reduction of partials into gsum[C][Ppad+4] (stat at [Ppad]); used before an all-reduce
+  static void reduce_partials(const ModelPlan& mp, int C, int S, const T* partial,
+                              const double* stat_part, T* gsum, cudaStream_t st);
+  // gradient assembly (+ priors) and leapfrog update.  If gsum != nullptr it is used
+  // instead of partial/stat_part (S ignored).
+  static void finalize(const ModelPlan& mp, int C, int S, const T* partial, const double* stat_part,
+                       const T* gsum, const T* hyper, long long N_total, T* theta_pad, T* mom_pad,
+                       T* grad_pad, const T* eps_dev, StepCoef cf, double* logp, double* stat_out,
+                       double* prior_part, unsigned* ticket, cudaStream_t st);
+  // momentum ~ N(0, I) (Philox) or copy of injected flat momentum; ke[c] = 0.5*sum p^2
+  static void momentum(const ModelPlan& mp, int C, uint64_t seed, uint64_t call, const T* injected_flat,
+                       T* mom_pad, double* ke, cudaStream_t st);
+  // Metropolis-Hastings select; writes flat theta and stats[C][4]
+  static void mh(const ModelPlan& mp, int C, uint64_t seed, uint64_t call, const T* u_in,
+                 const T* theta0_pad, const T* theta1_pad, const T* mom1_pad, const double* logp0,
+                 const double* logp1, const double* ke0, const double* stat0, const double* stat1,
+                 double* stat_cur, T* theta_flat, T* stats, cudaStream_t st);
+  // hyper chain: one CTA per chain
+  static void hyper_eval(const ModelPlan& mp, int C, const T* theta_flat, const T* hyper,
+                         const double* sse, long long N_total, T* logp, T* grad, cudaStream_t st);
+  static void hyper_step(const ModelPlan& mp, int C, const T* theta_flat, T* hyper, const double* sse,
+                         long long N_total, uint64_t seed, uint64_t call, int L, double epoch,
+                         double burnin, double hyper_step0, T* da_state, const T* mom_in,
+                         const T* u_in, T* stats, cudaStream_t st);
+  // predictor: samples already padded [S][Ppad]
+  static void predict(const ModelPlan& mp, const T* samples_pad, long long s0, long long S_chunk,
+                      long long S_total, const T* X, long long M, int rows_per_cta, T* out,
+                      T* moments, cudaStream_t st);
+};
+
+void launch_adapter_ucb(const float* eGrid, int eNumber, const float* lGrid, int lNumber,
+                        const float* prev, int n_hist, const float* Kinv, const float* KinvR, float s,
+                        float p, float rootbeta, float el, float eu, float Ll, float Lu,
+                        const float* sigma, float* out /*[3] e, L, ucb*/, void* workspace,
+                        cudaStream_t st);
+size_t adapter_workspace_bytes(int eNumber, int lNumber);
+
+}  // namespace tbnn

@@ -1,0 +1,148 @@
+"""GPU parity of the remaining hot-path rows: Philox momentum stream, adapter grid search
+(paramAdapter.gridSearch), posterior-predictive sweep (predictor.predict)."""
+import math
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import adapter as oad
+from oracle import targets
+from tensorbnn_b200 import workloads as wl
+import philox_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(arch, lik, dtype, chains=1):
+    from tensorbnn_b200.engine import Engine
+    return Engine(arch, lik, dtype=dtype, chains=chains)
+
+
+# ---------------------------------------------------------------------------- RNG
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_momentum_stream_matches_reference_philox(dtype):
+    arch, lik = wl.mlp_arch([3, 6, 5, 1], "dense", "squareprelu"), ("gaussian", 0.1)
+    eng = _engine(arch, lik, dtype, chains=3)
+    eng.set_data(np.zeros((2, 3)), np.zeros(2))
+    seed, call = 0x1234567890ABCDEF, 77
+    p, ke = eng.draw_momentum(seed, call)
+    p = p.cpu().numpy()
+    gen = philox_ref.normals_f32 if dtype == torch.float32 else philox_ref.normals_f64
+    tol = 2e-5 if dtype == torch.float32 else 1e-12
+    for c in range(3):
+        ref = gen(seed, philox_ref.STREAM_MAIN, call, c, eng.P)
+        assert np.abs(p[c] - ref).max() <= tol * max(1.0, np.abs(ref).max())
+        assert abs(ke[c].item() - 0.5 * np.sum(p[c].astype(np.float64) ** 2)) <= 1e-5 * ke[c].item()
+    # different call counter / chain => different stream
+    p2, _ = eng.draw_momentum(seed, call + 1)
+    assert not np.allclose(p2.cpu().numpy(), p)
+
+
+def test_momentum_is_standard_normal():
+    arch, lik = wl.mlp_arch([784, 20, 20, 1], "dense", "relu", "sigmoid"), ("bernoulli",)
+    eng = _engine(arch, lik, torch.float32, chains=8)
+    eng.set_data(np.zeros((2, 784)), np.zeros(2))
+    p, _ = eng.draw_momentum(42, 0)
+    x = p.cpu().numpy().ravel().astype(np.float64)
+    n = x.size
+    assert abs(x.mean()) < 5 / math.sqrt(n)
+    assert abs(x.var() - 1) < 5 * math.sqrt(2 / n)
+    assert abs(np.mean(x ** 3)) < 5 * math.sqrt(15 / n)
+    assert abs(np.mean(x ** 4) - 3) < 5 * math.sqrt(96 / n)
+
+
+# ---------------------------------------------------------------------------- adapter
+def _adapter_state(n_hist, seed, eN=40, Ll=100, Lu=2000, lStep=7):
+    rng = random.Random(seed)
+    ad = oad.OracleAdapter(1e-3, 500, 1e-4, 1e-2, eN, Ll, Lu, lStep, 10, 100, randomSteps=0, rng=rng)
+    nrng = np.random.default_rng(seed)
+    # drive the adapter with synthetic states until it has n_hist history points
+    st = [nrng.normal(size=(5, 3)), nrng.normal(size=(5, 1))]
+    guard = 0
+    while len(ad.previousGamma) < n_hist and guard < 5000:
+        st = [s + 0.01 * nrng.normal(size=s.shape) * (1 + 0.3 * math.sin(guard / 7.0)) for s in st]
+        ad.update(st)
+        guard += 1
+    return ad
+
+
+@pytest.mark.parametrize("n_hist,seed", [(1, 0), (3, 1), (12, 2), (30, 3)])
+def test_adapter_grid_search(n_hist, seed):
+    from tensorbnn_b200.engine import adapter_ucb
+    ad = _adapter_state(n_hist, seed)
+    args = (ad.previousGamma, ad.inverseR, ad.s, ad.inverse, ad.p, ad.rootbeta, ad.el, ad.eu, ad.sigma)
+    e_ref, L_ref = ad.gridSearch(*args)
+    e, L, ucb = adapter_ucb(0, ad.eGrid, ad.lGrid, np.array(ad.previousGamma, dtype=np.float32),
+                            ad.inverse, ad.inverseR[:, 0], ad.s, ad.p, ad.rootbeta, ad.el, ad.eu,
+                            ad.Ll, ad.Lu, ad.sigma)
+    surf = ad.ucb_surface(*args)                     # float64 surface, [lNumber, eNumber]
+    li = int(np.argmin(np.abs(ad.lGrid - L)))
+    ei = int(np.argmin(np.abs(ad.eGrid - e)))
+    assert ad.lGrid[li] == np.float32(L) and ad.eGrid[ei] == np.float32(e)   # a grid point
+    # the device choice is a maximiser of the surface up to float32 resolution of the UCB values
+    scale = max(1.0, float(np.abs(surf).max()))
+    assert surf[li, ei] >= surf.max() - 2e-5 * scale
+    if (e, L) != (float(e_ref), float(L_ref)):
+        lr = int(np.argmin(np.abs(ad.lGrid - L_ref)))
+        er = int(np.argmin(np.abs(ad.eGrid - e_ref)))
+        assert abs(surf[li, ei] - surf[lr, er]) <= 2e-5 * scale   # only near-ties may differ
+
+
+def test_adapter_first_maximum_tie_break():
+    """A flat surface (one history point at the grid centre with zero data) must return the FIRST
+    grid point in scan order (e fastest, L slowest), paramAdapter.py:184-190."""
+    from tensorbnn_b200.engine import adapter_ucb
+    eGrid = np.linspace(1e-4, 1e-2, 8).astype(np.float32)
+    lGrid = np.arange(100, 200, 10).astype(np.float32)
+    prev = np.array([[5.05e-3, 150.0]], dtype=np.float32)
+    # rootbeta = 0 and KinvR = 0 make the UCB identically zero
+    e, L, ucb = adapter_ucb(0, eGrid, lGrid, prev, np.ones((1, 1)), np.zeros(1), 1.0, 1.0, 0.0,
+                            1e-4, 1e-2, 100.0, 190.0, np.diag([6.25, 6.25]))
+    assert e == float(eGrid[0]) and L == float(lGrid[0]) and ucb == 0.0
+
+
+# ---------------------------------------------------------------------------- predictor
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("arch", [wl.mlp_arch([1, 64, 64, 64, 1], "dense", "squareprelu"),
+                                  wl.mlp_arch([5, 9, 3], "denseGaussian", "tanh"),
+                                  wl.mlp_arch([784, 20, 20, 1], "dense", "relu", "sigmoid")])
+def test_predict_matches_oracle(arch, dtype):
+    lik = ("fixed", 0.1)
+    rng = np.random.default_rng(0)
+    th0 = wl.init_theta(arch, seed=3)
+    S, M = 7, 333
+    samples = th0[None, :] + 0.05 * rng.normal(size=(S, th0.size))
+    D = arch[0][1]
+    X = rng.normal(size=(M, D))
+    eng = _engine(arch, lik, dtype)
+    out, mom = eng.predict(samples, X, want_out=True, want_moments=True)
+    out, mom = out.cpu().numpy(), mom.cpu().numpy()
+    np_dt = np.float32 if dtype == torch.float32 else np.float64
+    r = lambda a: torch.tensor(np.asarray(a).astype(np_dt).astype(np.float64))
+    ref = np.stack([targets.forward(arch, targets.unflatten_theta(arch, r(samples[s])), r(X)).numpy()
+                    for s in range(S)])
+    tol = 2e-5 if dtype == torch.float32 else 1e-11
+    assert np.abs(out - ref).max() <= tol * max(1.0, np.abs(ref).max())
+    assert np.all(mom[0] == S)
+    assert np.abs(mom[1] - ref.mean(axis=0)).max() <= 5 * tol * max(1.0, np.abs(ref).max())
+    var_ref = ref.var(axis=0)
+    assert np.abs(mom[2] / S - var_ref).max() <= 1e-4 * max(1e-12, var_ref.max()) + 10 * tol
+
+
+def test_predict_moments_only_many_samples():
+    """Fused mean/sd mode over more samples than one weight-staging chunk of rows."""
+    arch, lik = wl.mlp_arch([1, 16, 16, 1], "dense", "squareprelu"), ("gaussian", 0.1)
+    rng = np.random.default_rng(1)
+    th0 = wl.init_theta(arch, seed=4)
+    S, M = 200, 5000
+    samples = th0[None, :] + 0.05 * rng.normal(size=(S, th0.size))
+    X = np.linspace(-4, 4, M)[:, None]
+    eng = _engine(arch, lik, torch.float32)
+    _, mom = eng.predict(samples, X, want_out=False, want_moments=True)
+    out, _ = eng.predict(samples, X, want_out=True, want_moments=False)
+    out = out.cpu().numpy().astype(np.float64)
+    mom = mom.cpu().numpy()
+    assert np.abs(mom[1] - out.mean(axis=0)).max() <= 1e-5 * max(1.0, np.abs(out).max())
+    assert np.abs(mom[2] / S - out.var(axis=0)).max() <= 1e-4 * out.var(axis=0).max() + 1e-9

@@ -1,0 +1,317 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): log-posterior and gradient within 1e-5
+relative in fp32 (1e-10 in fp64); fixed-momentum L-step trajectory endpoints
+within 1e-4.  "Relative" for a gradient vector means max|g - g_ref| <= tol *
+max|g_ref| (elementwise relative error is undefined for near-zero entries).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import analytic, hmc, targets
+from tensorbnn_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.float64: 1e-10}
+
+
+def _engine(arch, lik, dtype, chains=1):
+    from tensorbnn_b200.engine import Engine
+    return Engine(arch, lik, dtype=dtype, chains=chains)
+
+
+ARCHS = {
+    "c1a": (wl.mlp_arch([1, 10, 10, 10, 1], "denseGaussian", "tanh"), ("fixed", 0.1)),
+    "c1b": (wl.mlp_arch([1, 10, 10, 10, 1], "dense", "relu"), ("gaussian", 0.1)),
+    "bern": (wl.mlp_arch([7, 5, 4, 1], "dense", "relu", "sigmoid"), ("bernoulli",)),
+    "c2s": (wl.mlp_arch([784, 20, 20, 1], "dense", "relu", "sigmoid"), ("bernoulli",)),
+    "sqp": (wl.mlp_arch([3, 6, 6, 2], "dense", "squareprelu"), ("gaussian", 0.2)),
+    "c3s": (wl.mlp_arch([1, 64, 64, 64, 1], "dense", "squareprelu"), ("gaussian", 0.1)),
+    "prelu": (wl.mlp_arch([3, 6, 5, 1], "denseGaussian", "prelu"), ("fixed", 0.3)),
+    "mixed": ([("dense", 4, 6), ("elu",), ("denseGaussian", 6, 5), ("Exp",), ("dense", 5, 3),
+               ("leakyrelu", 0.3), ("dense", 3, 1), ("sigmoid",)], ("bernoulli",)),
+    "c4s": (wl.mlp_arch([32, 128, 128, 128, 1], "dense", "relu"), ("gaussian", 0.1)),
+    "wide_out": (wl.mlp_arch([5, 9, 3], "denseGaussian", "tanh"), ("gaussian", 0.5)),
+}
+
+
+def problem(key, N, seed=0, chains=1):
+    arch, lik = ARCHS[key]
+    rng = np.random.default_rng(seed)
+    D = arch[0][1]
+    out = [l for l in arch if l[0] in ("dense", "denseGaussian")][-1][2]
+    X = rng.random((N, D)) if D > 100 else rng.normal(size=(N, D))
+    if lik[0] == "bernoulli":
+        Y = (rng.random(N) > 0.5).astype(np.float64)
+    else:
+        Y = rng.normal(size=(N, out))
+    thetas, hypers = [], []
+    for c in range(chains):
+        th = wl.init_theta(arch, seed=seed + 5 + 17 * c) * 0.7
+        th = th + 0.05 * rng.normal(size=th.size)
+        hy = wl.init_hyper(arch, lik)
+        hy = hy + 0.05 * rng.normal(size=hy.size)
+        thetas.append(th)
+        hypers.append(hy)
+    return arch, lik, X, Y, np.stack(thetas), np.stack(hypers)
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---------------------------------------------------------------------------- main target
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("key,N", [("c1a", 11), ("c1b", 11), ("bern", 37), ("c2s", 150), ("sqp", 61),
+                                   ("c3s", 200), ("prelu", 29), ("mixed", 45), ("c4s", 70),
+                                   ("wide_out", 33), ("c1a", 1), ("bern", 3), ("c3s", 4096)])
+def test_logp_grad(key, N, dtype):
+    arch, lik, X, Y, TH, HY = problem(key, N, chains=2)
+    eng = _engine(arch, lik, dtype, chains=2)
+    eng.set_data(X, Y)
+    lp, g, stat = eng.logp_grad(TH, HY)
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    # the kernel sees inputs rounded to its dtype: evaluate the fp64 oracle on the same rounded values
+    np_dt = np.float32 if dtype == torch.float32 else np.float64
+    Xr, Yr = X.astype(np_dt).astype(np.float64), Y.astype(np_dt).astype(np.float64)
+    for c in range(2):
+        th, hy = TH[c].astype(np_dt).astype(np.float64), HY[c].astype(np_dt).astype(np.float64)
+        lp_ref, g_ref = analytic.main_value_and_grad(arch, lik, th, hy, Xr, Yr)
+        assert abs(lp[c] - lp_ref) <= TOL[dtype] * max(1.0, abs(lp_ref)), (key, c, lp[c], lp_ref)
+        assert rel(g[c], g_ref) <= TOL[dtype], (key, c, rel(g[c], g_ref))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_logp_grad_matches_autograd_oracle(dtype):
+    """Same check against the autograd restatement (oracle/targets.py)."""
+    arch, lik, X, Y, TH, HY = problem("c2s", 96)
+    eng = _engine(arch, lik, dtype)
+    eng.set_data(X, Y)
+    lp, g, _ = eng.logp_grad(TH, HY)
+    np_dt = np.float32 if dtype == torch.float32 else np.float64
+    f64 = lambda a: torch.tensor(a.astype(np_dt).astype(np.float64))
+    lp_ref, g_ref = targets.main_value_and_grad(arch, lik, f64(TH[0]), f64(HY[0]), f64(X), f64(Y))
+    assert abs(lp.item() - lp_ref.item()) <= TOL[dtype] * abs(lp_ref.item())
+    assert rel(g.cpu().numpy()[0], g_ref.numpy()) <= TOL[dtype]
+
+
+def test_padding_stays_zero_and_inputs_untouched():
+    arch, lik, X, Y, TH, HY = problem("mixed", 45)
+    eng = _engine(arch, lik, torch.float32)
+    eng.set_data(X, Y)
+    th = eng.tensor(TH)
+    th0 = th.clone()
+    eng.logp_grad(th, HY)
+    assert torch.equal(th, th0)
+
+
+# ---------------------------------------------------------------------------- hyper target
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("key,N", [("c1a", 11), ("c1b", 11), ("sqp", 61), ("prelu", 29), ("c3s", 200),
+                                   ("bern", 37)])
+def test_hyper_logp_grad(key, N, dtype):
+    arch, lik, X, Y, TH, HY = problem(key, N, chains=2)
+    eng = _engine(arch, lik, dtype, chains=2)
+    eng.set_data(X, Y)
+    lp, g = eng.hyper_logp_grad(TH, HY)
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    np_dt = np.float32 if dtype == torch.float32 else np.float64
+    Xr, Yr = X.astype(np_dt).astype(np.float64), Y.astype(np_dt).astype(np.float64)
+    tol = 2e-5 if dtype == torch.float32 else 1e-10
+    for c in range(2):
+        th, hy = TH[c].astype(np_dt).astype(np.float64), HY[c].astype(np_dt).astype(np.float64)
+        lp_ref, g_ref = analytic.hyper_value_and_grad(arch, lik, th, hy, Xr, Yr)
+        assert abs(lp[c] - lp_ref) <= tol * max(1.0, abs(lp_ref)), (key, lp[c], lp_ref)
+        assert rel(g[c], g_ref) <= tol, (key, rel(g[c], g_ref))
+
+
+# ---------------------------------------------------------------------------- trajectories
+def _oracle_traj(arch, lik, X, Y, th, hy, p, eps, L, tdt):
+    t = lambda a: torch.tensor(np.asarray(a), dtype=tdt)
+    vg = hmc.make_main_vg(arch, lik, t(hy), t(X), t(Y))
+    return hmc.leapfrog(vg, t(th), t(p), eps, L)
+
+
+@pytest.mark.parametrize("key,N,eps,L", [("c1a", 11, 1e-3, 100), ("c1b", 11, 1e-3, 60),
+                                         ("bern", 37, 5e-3, 50), ("c2s", 128, 1e-3, 25),
+                                         ("c3s", 128, 1e-3, 25)])
+def test_trajectory_fp64(key, N, eps, L):
+    arch, lik, X, Y, TH, HY = problem(key, N)
+    rng = np.random.default_rng(3)
+    p0 = rng.normal(size=TH.shape)
+    eng = _engine(arch, lik, torch.float64)
+    eng.set_data(X, Y)
+    th1, p1, lp1, g1 = eng.trajectory(TH, HY, p0, eps, L)
+    rth, rp, rlp, rg = _oracle_traj(arch, lik, X, Y, TH[0], HY[0], p0[0], eps, L, torch.float64)
+    assert rel(th1.cpu().numpy()[0], rth.numpy()) <= 1e-9
+    assert rel(p1.cpu().numpy()[0], rp.numpy()) <= 1e-8
+    assert abs(lp1.item() - rlp.item()) <= 1e-9 * max(1.0, abs(rlp.item()))
+    assert rel(g1.cpu().numpy()[0], rg.numpy()) <= 1e-8
+
+
+@pytest.mark.parametrize("key,N,eps,L", [("c1a", 11, 1e-3, 100), ("c1b", 11, 1e-3, 60),
+                                         ("bern", 37, 5e-3, 50), ("c2s", 128, 1e-3, 25),
+                                         ("c3s", 128, 1e-3, 25)])
+def test_trajectory_fp32_endpoints(key, N, eps, L):
+    """north_star: fixed-momentum L-step trajectory endpoints within 1e-4 (fp32 kernel vs fp64 oracle
+    started from the same fp32-rounded state)."""
+    arch, lik, X, Y, TH, HY = problem(key, N)
+    rng = np.random.default_rng(3)
+    p0 = rng.normal(size=TH.shape)
+    r32 = lambda a: np.asarray(a).astype(np.float32).astype(np.float64)
+    eng = _engine(arch, lik, torch.float32)
+    eng.set_data(X, Y)
+    th1, p1, lp1, _ = eng.trajectory(TH, HY, p0, eps, L)
+    rth, rp, rlp, _ = _oracle_traj(arch, lik, r32(X), r32(Y), r32(TH[0]), r32(HY[0]), r32(p0[0]),
+                                   float(np.float32(eps)), L, torch.float64)
+    assert np.abs(th1.cpu().numpy()[0] - rth.numpy()).max() <= 1e-4 * max(1.0, np.abs(rth.numpy()).max())
+    assert np.abs(p1.cpu().numpy()[0] - rp.numpy()).max() <= 1e-4 * max(1.0, np.abs(rp.numpy()).max())
+    assert abs(lp1.item() - rlp.item()) <= 1e-4 * max(1.0, abs(rlp.item()))
+
+
+def test_trajectory_reversibility_fp64():
+    """Leapfrog is time-reversible: run L steps, flip the momentum, run L steps, recover the start."""
+    arch, lik, X, Y, TH, HY = problem("c1a", 11)
+    rng = np.random.default_rng(4)
+    p0 = rng.normal(size=TH.shape)
+    eng = _engine(arch, lik, torch.float64)
+    eng.set_data(X, Y)
+    th1, p1, _, _ = eng.trajectory(TH, HY, p0, 2e-3, 40)
+    th2, p2, _, _ = eng.trajectory(th1, HY, -p1, 2e-3, 40)
+    assert rel(th2.cpu().numpy(), TH) <= 1e-10
+    assert rel(-p2.cpu().numpy(), p0) <= 1e-10
+
+
+def test_trajectory_per_chain_step_sizes():
+    arch, lik, X, Y, TH, HY = problem("sqp", 61, chains=3)
+    rng = np.random.default_rng(5)
+    p0 = rng.normal(size=TH.shape)
+    eps = np.array([1e-3, 2e-3, 5e-4])
+    eng = _engine(arch, lik, torch.float64, chains=3)
+    eng.set_data(X, Y)
+    th1, p1, lp1, _ = eng.trajectory(TH, HY, p0, eps, 20)
+    for c in range(3):
+        rth, rp, rlp, _ = _oracle_traj(arch, lik, X, Y, TH[c], HY[c], p0[c], eps[c], 20, torch.float64)
+        assert rel(th1.cpu().numpy()[c], rth.numpy()) <= 1e-9
+        assert abs(lp1[c].item() - rlp.item()) <= 1e-9 * max(1.0, abs(rlp.item()))
+
+
+# ---------------------------------------------------------------------------- HMC transition
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_hmc_step_injected(dtype):
+    arch, lik, X, Y, TH, HY = problem("c1b", 11, chains=4)
+    rng = np.random.default_rng(6)
+    p0 = rng.normal(size=TH.shape)
+    eps, L = 2e-3, 30
+    np_dt = np.float32 if dtype == torch.float32 else np.float64
+    r = lambda a: np.asarray(a).astype(np_dt).astype(np.float64)
+    # oracle log-accept ratios first, then choose u so that two chains accept and two reject
+    refs = []
+    for c in range(4):
+        t = lambda a: torch.tensor(r(a))
+        vg = hmc.make_main_vg(arch, lik, t(HY[c]), t(X), t(Y))
+        refs.append(hmc.hmc_step(vg, t(TH[c]), t(p0[c]), 0.5, float(np_dt(eps)), L))
+    lars = np.array([x[1].item() for x in refs])
+    u = np.empty(4)
+    u[0::2] = np.exp(np.minimum(lars[0::2], 0.0) - 1.0)                       # accept
+    u[1::2] = np.minimum(1 - 1e-6, np.exp(np.minimum(lars[1::2], 0.0)) * 1.5 + 1e-3)  # reject if lar<0
+    eng = _engine(arch, lik, dtype, chains=4)
+    eng.set_data(X, Y)
+    th = eng.tensor(TH).clone()
+    stats = eng.hmc_step(th, HY, 1, 0, eps, L, momentum=p0, u=u).cpu().numpy()
+    tol = 2e-4 if dtype == torch.float32 else 1e-8
+    for c in range(4):
+        new, lar, prob, _, prop, _ = refs[c]
+        assert abs(stats[c, 0] - lar.item()) <= tol * max(1.0, abs(lar.item())), (c, stats[c], lar)
+        assert abs(stats[c, 1] - prob.item()) <= tol
+        acc_ref = math.log(u[c]) < lar.item()
+        assert bool(stats[c, 2]) == acc_ref
+        expect = prop.numpy() if acc_ref else r(TH[c])
+        assert np.abs(th.cpu().numpy()[c] - expect).max() <= tol * max(1.0, np.abs(expect).max())
+        sjd_ref = float(np.sum((prop.numpy() - r(TH[c])) ** 2)) if acc_ref else 0.0
+        assert abs(stats[c, 3] - sjd_ref) <= 10 * tol * max(1e-12, sjd_ref) + 1e-30
+
+
+def test_hmc_step_divergent_rejects():
+    """A divergent trajectory (NaN / -inf log-accept ratio) must be rejected (TFP safe_sum)."""
+    arch, lik, X, Y, TH, HY = problem("c1a", 11)
+    eng = _engine(arch, lik, torch.float32)
+    eng.set_data(X, Y)
+    th = eng.tensor(TH).clone()
+    p0 = np.full(TH.shape, 1e3)
+    stats = eng.hmc_step(th, HY, 1, 0, 10.0, 20, momentum=p0, u=np.array([0.5])).cpu().numpy()
+    assert stats[0, 2] == 0.0
+    assert torch.equal(th, eng.tensor(TH))
+
+
+def test_hmc_sampler_standard_normal_moments():
+    """Sampler statistics on a Gaussian toy target: one Gaussian dense layer 1->1 with zero data weight
+    has theta ~ N(0, I) under its prior alone (sigma = 1, N tiny with huge fixed sd)."""
+    arch, lik = [("denseGaussian", 1, 1)], ("fixed", 1e6)
+    X, Y = np.zeros((1, 1)), np.zeros(1)
+    C = 512
+    eng = _engine(arch, lik, torch.float32, chains=C)
+    eng.set_data(X, Y)
+    hy = np.tile(wl.init_hyper(arch, lik), (C, 1))
+    th = eng.tensor(np.zeros((C, 2))).clone()
+    draws = []
+    for it in range(60):
+        eng.hmc_step(th, hy, 1234, it, 0.3, 5)
+        if it >= 10:
+            draws.append(th.cpu().numpy().copy())
+    d = np.concatenate(draws)
+    assert abs(d.mean()) < 0.05
+    assert abs(d.var() - 1.0) < 0.08
+
+
+# ---------------------------------------------------------------------------- hyper chain
+@pytest.mark.parametrize("key,N", [("c1b", 11), ("sqp", 61), ("c1a", 11)])
+def test_hyper_step_injected_fp64(key, N):
+    arch, lik, X, Y, TH, HY = problem(key, N)
+    rng = np.random.default_rng(8)
+    H = HY.shape[1]
+    p0 = rng.normal(size=(1, H))
+    eng = _engine(arch, lik, torch.float64)
+    eng.set_data(X, Y)
+    step0, L, epoch, burnin = 1e-3, 15, 3.0, 100.0
+    t = lambda a: torch.tensor(np.asarray(a))
+    vg = hmc.make_hyper_vg(arch, lik, t(TH[0]), t(X), t(Y))
+    for u in (1e-12, 1 - 1e-9):
+        hy = eng.tensor(HY).clone()
+        da = eng.tensor(np.array([[0.1, -0.2, 2e-3]])).clone()
+        stats = eng.hyper_step(TH, hy, 1, 0, L, epoch, burnin, step0, da, momentum=p0,
+                               u=np.array([u])).cpu().numpy()
+        new, lar, prob, acc, _, _ = hmc.hmc_step(vg, t(HY[0]), t(p0[0]), u, 2e-3, L)
+        assert abs(stats[0, 0] - lar.item()) <= 1e-8 * max(1.0, abs(lar.item()))
+        assert rel(hy.cpu().numpy()[0], new.numpy()) <= 1e-9
+        hh, leb, st = hmc.dual_averaging(epoch, prob.item(), 0.1, -0.2, 2e-3, step0, burnin)
+        got = da.cpu().numpy()[0]
+        assert abs(got[0] - hh) <= 1e-12 and abs(got[1] - leb) <= 1e-12 and abs(got[2] - st) <= 1e-12 * st
+
+
+def test_hyper_dual_averaging_freezes_after_burnin():
+    arch, lik, X, Y, TH, HY = problem("c1b", 11)
+    eng = _engine(arch, lik, torch.float64)
+    eng.set_data(X, Y)
+    hy = eng.tensor(HY).clone()
+    da = eng.tensor(np.array([[0.0, 0.0, 3e-3]])).clone()
+    eng.hyper_step(TH, hy, 1, 0, 5, 90.0, 100.0, 1e-3, da)       # m = 91 >= 0.8*100: frozen
+    assert da.cpu().numpy()[0, 2] == 3e-3
+
+
+# ---------------------------------------------------------------------------- edge cases / errors
+def test_errors_are_loud():
+    from tensorbnn_b200.engine import Engine
+    arch, lik = ARCHS["c1a"]
+    eng = Engine(arch, lik)
+    with pytest.raises(RuntimeError):
+        eng.logp_grad(np.zeros((1, eng.P)), np.zeros((1, eng.H)))   # no data yet
+    with pytest.raises(RuntimeError):
+        Engine([("relu",)], ("bernoulli",))
+    with pytest.raises(RuntimeError):
+        Engine([("dense", 3, 4), ("dense", 5, 1)], ("bernoulli",))
