@@ -120,6 +120,12 @@ int tbnn_hmc_step(tbnn_handle* h, void* theta, const void* hyper, uint64_t seed,
 int tbnn_draw_momentum(tbnn_handle* h, uint64_t seed, uint64_t counter, void* momentum_out, void* ke_out,
                        void* stream);
 
+/* Measurement hook for bench.py's roofline: launches the likelihood row-sweep kernel (the dominant
+ * kernel of a leapfrog step) `iters` times on `stream` for theta[C][P], each launch bracketed by CUDA
+ * events on that stream, and returns the average and minimum launch duration in milliseconds. */
+int tbnn_time_sweep(tbnn_handle* h, const void* theta, int iters, float* avg_ms, float* min_ms,
+                    void* stream);
+
 /* One HMC transition of the hyper chain + the hand-rolled dual averaging of
  * network.py:442-471 (constants :241-248).  hyper[C][H] updated in place.
  * da_state[C][3] (dtype) = {h, logEpsilonBar, hyper_step_size}, updated in place.

@@ -171,7 +171,8 @@ static int plan_structure(const tbnn_desc* d, ModelPlan& mp) {
 
 // Shared-memory layout for a given tile height.  train: with z / dZ buffers and gradient
 // accumulators; predict: forward only with `acc_elems` accumulator elements.
-static size_t plan_smem(ModelPlan& mp, int TR, bool train, bool w_in_smem, int acc_elems, size_t esz) {
+static size_t plan_smem(ModelPlan& mp, int TR, bool train, bool w_in_smem, int acc_elems, size_t esz,
+                        bool g_in_smem = true) {
   mp.TR = TR;
   int cur = 0, ldmax = 4;
   mp.offX = cur; cur += TR * mp.ld0;
@@ -193,7 +194,8 @@ static size_t plan_smem(ModelPlan& mp, int TR, bool train, bool w_in_smem, int a
   mp.offDb = cur; if (train) cur += TR * ldmax;
   mp.offScr = cur; cur += scr;
   if (w_in_smem) { mp.offW = cur; cur += mp.Ppad; } else mp.offW = -1;
-  mp.offG = cur; cur += train ? mp.Ppad : pad4(acc_elems);
+  if (train && !g_in_smem) mp.offG = -1;
+  else { mp.offG = cur; cur += train ? mp.Ppad : pad4(acc_elems); }
   const int per8 = (int)(8 / esz);
   cur = (cur + per8 - 1) / per8 * per8;
   mp.offRed = cur; cur += 64 * per8;
@@ -202,14 +204,15 @@ static size_t plan_smem(ModelPlan& mp, int TR, bool train, bool w_in_smem, int a
 }
 
 static int plan_train(ModelPlan& mp, size_t esz) {
-  for (int w = 1; w >= 0; --w)
+  // preference: weights + accumulators in smem; weights streamed from global (L1/L2);
+  // accumulators in the CTA's global partial slice as well (very large layers / fp64)
+  const bool opts[3][2] = {{true, true}, {false, true}, {false, false}};
+  for (int o = 0; o < 3; ++o)
     for (int TR = 64; TR >= 4; TR -= 4)
-      if (plan_smem(mp, TR, true, w == 1, 0, esz) <= SMEM_LIMIT) {
-        if (w == 1 && TR < 8) continue;   // prefer streaming weights over degenerate tiles
+      if (plan_smem(mp, TR, true, opts[o][0], 0, esz, opts[o][1]) <= SMEM_LIMIT) {
+        if (o < 2 && TR < 8) continue;   // prefer the next option over degenerate tiles
         return 0;
       }
-  for (int TR = 4; TR >= 4; TR -= 4)
-    if (plan_smem(mp, TR, true, true, 0, esz) <= SMEM_LIMIT) return 0;
   return fail("network too large for the shared-memory tile engine");
 }
 
@@ -514,6 +517,46 @@ extern "C" int tbnn_draw_momentum(tbnn_handle* h, uint64_t seed, uint64_t counte
   h->launches += 2;
   CU(cudaGetLastError());
   return 0;
+}
+
+template <typename T>
+static int time_sweep_impl(tbnn_handle* h, const void* theta, int iters, float* avg_ms, float* min_ms,
+                           cudaStream_t st) {
+  const ModelPlan& mp = h->mp;
+  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st);
+  h->launches++;
+  std::vector<cudaEvent_t> ev(2 * iters);
+  for (auto& e : ev) CU(cudaEventCreate(&e));
+  for (int i = 0; i < iters; ++i) {
+    CU(cudaEventRecord(ev[2 * i], st));
+    Launch<T>::partial(mp, h->C, h->S, true, (const T*)h->theta_pad, (const T*)h->X, (const T*)h->Y, h->N,
+                       (T*)h->partial, h->stat_part, st);
+    CU(cudaEventRecord(ev[2 * i + 1], st));
+    h->launches++;
+  }
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  double tot = 0.0;
+  float mn = 1e30f;
+  for (int i = 0; i < iters; ++i) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+    tot += ms;
+    mn = std::min(mn, ms);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (avg_ms) *avg_ms = (float)(tot / iters);
+  if (min_ms) *min_ms = mn;
+  return 0;
+}
+
+extern "C" int tbnn_time_sweep(tbnn_handle* h, const void* theta, int iters, float* avg_ms, float* min_ms,
+                               void* stream) {
+  CK(check_ready(h));
+  if (!theta || iters < 1) return fail("bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->dtype == TBNN_F32 ? time_sweep_impl<float>(h, theta, iters, avg_ms, min_ms, st)
+                              : time_sweep_impl<double>(h, theta, iters, avg_ms, min_ms, st);
 }
 
 // SSE of the current theta (forward-only sweep) for the Gaussian likelihood's hyper term

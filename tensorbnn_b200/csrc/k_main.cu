@@ -65,7 +65,8 @@ k_partial(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ the
   const T* thg = theta_pad + (size_t)c * mp.Ppad;
   TileCtx<T> cx;
   cx.sm = sm;
-  cx.G = sm + mp.offG;
+  // accumulators: shared memory, or (huge layers) this CTA's slice of the global partial buffer
+  cx.G = mp.offG >= 0 ? sm + mp.offG : partial + ((size_t)c * S + s) * mp.Ppad;
   if (mp.offW >= 0) {
     T* Ws = sm + mp.offW;
     for (int i = 4 * threadIdx.x; i < mp.Ppad; i += 4 * blockDim.x) {
@@ -97,7 +98,7 @@ k_partial(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ the
       stat += lik_phase<T>(mp, cx, Y, row0, nr, sm + mp.offDa);
     }
   }
-  if (BWD) {
+  if (BWD && mp.offG >= 0) {
     T* out = partial + ((size_t)c * S + s) * mp.Ppad;
     for (int i = 4 * threadIdx.x; i < mp.Ppad; i += 4 * blockDim.x) {
       T v[4];

@@ -134,6 +134,13 @@ class Engine(object):
         _lib.check(self.lib.tbnn_draw_momentum(self.h, int(seed), int(counter), _ptr(p), _ptr(ke), _stream()))
         return p, ke
 
+    def time_sweep(self, theta, iters=20):
+        """(avg_ms, min_ms) of the row-sweep kernel, CUDA events on the launching stream."""
+        theta = self.tensor(theta, (self.chains, self.P))
+        a, m = C.c_float(), C.c_float()
+        _lib.check(self.lib.tbnn_time_sweep(self.h, _ptr(theta), int(iters), C.byref(a), C.byref(m), _stream()))
+        return float(a.value), float(m.value)
+
     def hyper_step(self, theta, hyper, seed, counter, hyperL, epoch, burnin, hyper_step0, da_state,
                    momentum=None, u=None, stats=None):
         """hyper [C,H] and da_state [C,3] = (h, logEpsilonBar, step) are updated IN PLACE."""
