@@ -272,7 +272,8 @@ extern "C" int tbnn_create(const tbnn_desc* d, tbnn_handle** out) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, d->device));
   h->num_sms = prop.multiProcessorCount;
-  if (plan_structure(d, h->mp) || plan_train(h->mp, h->esz) || plan_predict(h)) { delete h; return 1; }
+  if (plan_structure(d, h->mp) || plan_train(h->mp, h->esz)) { delete h; return 1; }
+  if (plan_predict(h)) h->pp_rows = 0;   // predictor unavailable for this network/dtype; tbnn_predict reports it
   const ModelPlan& mp = h->mp;
   const size_t C = h->C, e = h->esz, pp = (size_t)mp.Ppad;
   h->nblkF = (mp.Ppad + 255) / 256;
@@ -707,6 +708,7 @@ extern "C" int tbnn_predict(tbnn_handle* h, const void* samples, int64_t S, cons
   if (!h || !samples || !Xtest) return fail("null argument");
   if (S < 1 || M < 1) return fail("S and M must be positive");
   if (!out && !moments) return fail("one of out / moments must be given");
+  if (h->pp_rows <= 0) return fail("network too large for the predictor kernel (weights must fit in shared memory)");
   CU(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   return h->dtype == TBNN_F32 ? predict_impl<float>(h, samples, S, Xtest, M, out, moments, st)
