@@ -268,7 +268,7 @@ def main():
     abytes = algorithmic_bytes_per_step(cfg, eng.P, 4, C)
     achieved = abytes / (avg_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "k_partial<float,true>",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": eng.sweep_info()["kernel"], "sweep": eng.sweep_info(),
             "launch_ms": avg_ms, "launch_ms_min": min_ms, "algorithmic_bytes_per_launch": abytes,
             "peak_source": peak_src,
             "fp32_tflops": C * flops_per_chain_step(cfg) / (avg_ms * 1e-3) / 1e12,

@@ -51,6 +51,10 @@ enum { TBNN_LIK_GAUSSIAN = 0,       /* likelihood.py:63  sigma = hyper[-1]^2 */
 
 enum { TBNN_F32 = 0, TBNN_F64 = 1 };
 
+/* tbnn_desc.flags: kernel-selection overrides used by the parity tests (results are the same
+ * target either way; only the kernel that computes it changes). */
+enum { TBNN_FLAG_NO_WIDE = 1 /* never use the wide-first-layer row sweep */ };
+
 typedef struct {
   int32_t kind;    /* TBNN_DENSE_* or TBNN_ACT_* */
   int32_t in_dim;  /* dense: inputs; activations with slopes: width; else 0 */
@@ -66,7 +70,7 @@ typedef struct {
   int32_t dtype;      /* TBNN_F32 / TBNN_F64 */
   int32_t chains;     /* C independent chains batched per launch (reference: 1) */
   int32_t device;     /* CUDA ordinal */
-  int32_t flags;      /* reserved, 0 */
+  int32_t flags;      /* TBNN_FLAG_* (0 = defaults) */
 } tbnn_desc;
 
 const char* tbnn_last_error(void);
@@ -79,6 +83,16 @@ int tbnn_num_params(const tbnn_handle* h);  /* P */
 int tbnn_num_hypers(const tbnn_handle* h);  /* H */
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t tbnn_launch_count(const tbnn_handle* h);
+
+/* Which row-sweep kernel the handle planned: kernel_kind 0 = generic tile engine (k_partial),
+ * 1 = wide-first-layer FFMA sweep (k_sweep_wide); CTAs per chain (valid after set_data), rows per
+ * tile / pass, dynamic shared memory per CTA.  Any out pointer may be NULL. */
+int tbnn_sweep_info(const tbnn_handle* h, int* kernel_kind, int* ctas_per_chain, int* rows_per_tile,
+                    int* smem_bytes);
+
+/* Developer aid: clock64 phase marks of CTA 0 of one (warm) wide-sweep launch; clocks_host64[0] =
+ * number of marks, followed by the marks.  Fails unless tbnn_sweep_info reports kernel_kind 1. */
+int tbnn_wide_profile(tbnn_handle* h, const void* theta, long long* clocks_host64, void* stream);
 
 /* Training set resident in HBM (network.py:41-45: tf.constant).  X[N][D] row-major,
  * Y[N][out].  set_data borrows device pointers; set_data_host copies HOST buffers

@@ -13,9 +13,10 @@ ACT = {"relu": 10, "tanh": 11, "sigmoid": 12, "Exp": 13, "elu": 14, "leakyrelu":
 DENSE = {"dense": DENSE_CAUCHY, "denseGaussian": DENSE_GAUSSIAN}
 LIK = {"gaussian": 0, "fixed": 1, "bernoulli": 2}
 F32, F64 = 0, 1
+FLAG_NO_WIDE = 1   # tbnn_desc.flags: never use the wide-first-layer row sweep
 
 EXPORTS = ["tbnn_last_error", "tbnn_version", "tbnn_create", "tbnn_destroy", "tbnn_num_params",
-           "tbnn_num_hypers", "tbnn_launch_count", "tbnn_set_data", "tbnn_set_data_host",
+           "tbnn_num_hypers", "tbnn_launch_count", "tbnn_sweep_info", "tbnn_wide_profile", "tbnn_set_data", "tbnn_set_data_host",
            "tbnn_logp_grad", "tbnn_hyper_logp_grad", "tbnn_trajectory", "tbnn_hmc_step",
            "tbnn_draw_momentum", "tbnn_time_sweep", "tbnn_hyper_step", "tbnn_adapter_ucb", "tbnn_predict", "tbnn_comm_unique_id",
            "tbnn_comm_init"]
@@ -55,6 +56,9 @@ def load():
     lib.tbnn_num_hypers.argtypes = [vp]
     lib.tbnn_launch_count.argtypes = [vp]
     lib.tbnn_launch_count.restype = i64
+    pi = C.POINTER(C.c_int)
+    lib.tbnn_sweep_info.argtypes = [vp, pi, pi, pi, pi]
+    lib.tbnn_wide_profile.argtypes = [vp, vp, C.POINTER(C.c_longlong), vp]
     lib.tbnn_set_data.argtypes = [vp, vp, vp, i64]
     lib.tbnn_set_data_host.argtypes = [vp, vp, vp, i64, vp]
     lib.tbnn_logp_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -78,7 +82,7 @@ def check(rc):
         raise RuntimeError("libtbnn: " + load().tbnn_last_error().decode("utf-8", "replace"))
 
 
-def make_desc(arch, lik, dtype_code, chains, device):
+def make_desc(arch, lik, dtype_code, chains, device, flags=0):
     """arch / lik in the vocabulary of tensorbnn_b200.workloads."""
     n = len(arch)
     layers = (LayerDesc * n)()
@@ -95,5 +99,5 @@ def make_desc(arch, lik, dtype_code, chains, device):
         else:
             raise ValueError("layer kind %r is not supported by the CUDA path" % (k,))
     d = Desc(n, layers, LIK[lik[0]], float(lik[1]) if lik[0] == "fixed" else 0.0, dtype_code,
-             int(chains), int(device), 0)
+             int(chains), int(device), int(flags))
     return d, layers

@@ -65,6 +65,8 @@ struct tbnn_handle {
   int dtype = TBNN_F32, C = 1, device = 0, num_sms = 148;
   size_t esz = 4;
   ModelPlan mp;        // training plan
+  ModelPlan wp;        // wide-first-layer sweep plan (fp32 only)
+  bool use_wide = false;
   ModelPlan pp;        // predictor (forward-only) plan
   int pp_rows = 0;     // rows per CTA of the predictor
   // data
@@ -172,11 +174,11 @@ static int plan_structure(const tbnn_desc* d, ModelPlan& mp) {
 // Shared-memory layout for a given tile height.  train: with z / dZ buffers and gradient
 // accumulators; predict: forward only with `acc_elems` accumulator elements.
 static size_t plan_smem(ModelPlan& mp, int TR, bool train, bool w_in_smem, int acc_elems, size_t esz,
-                        bool g_in_smem = true) {
+                        bool g_in_smem = true, int x_bufs = 1, int g_skip = 0, int scr_min = 0) {
   mp.TR = TR;
   int cur = 0, ldmax = 4;
-  mp.offX = cur; cur += TR * mp.ld0;
-  int scr = 0;
+  mp.offX = cur; cur += x_bufs * TR * mp.ld0;
+  int scr = scr_min;
   for (int l = 0; l < mp.nb; ++l) {
     BlockPlan& b = mp.b[l];
     b.offS = cur; cur += TR * b.ld_out;
@@ -195,7 +197,7 @@ static size_t plan_smem(ModelPlan& mp, int TR, bool train, bool w_in_smem, int a
   mp.offScr = cur; cur += scr;
   if (w_in_smem) { mp.offW = cur; cur += mp.Ppad; } else mp.offW = -1;
   if (train && !g_in_smem) mp.offG = -1;
-  else { mp.offG = cur; cur += train ? mp.Ppad : pad4(acc_elems); }
+  else { mp.offG = cur; cur += train ? mp.Ppad - g_skip : pad4(acc_elems); }
   const int per8 = (int)(8 / esz);
   cur = (cur + per8 - 1) / per8 * per8;
   mp.offRed = cur; cur += 64 * per8;
@@ -214,6 +216,37 @@ static int plan_train(ModelPlan& mp, size_t esz) {
         return 0;
       }
   return fail("network too large for the shared-memory tile engine");
+}
+
+// Wide-first-layer sweep (k_wide.cu): 16-row passes with two X buffers; W1 accumulators in
+// registers; blocks >= 1 are a narrow tail with [RB]-row batch buffers (wp.TR = RB).
+static bool plan_wide(const ModelPlan& mp, ModelPlan& wp) {
+  if (!wide_supported(mp)) return false;
+  const int WTR = wide_rows_per_pass();
+  for (int RB = 4 * WTR; RB >= WTR; RB -= WTR) {
+    wp = mp;
+    wp.TR = RB;
+    int cur = 0;
+    wp.offX = cur; cur += 2 * WTR * wp.ld0;
+    for (int l = 0; l < wp.nb; ++l) {
+      BlockPlan& b = wp.b[l];
+      b.ksplit = 1;
+      b.offS = cur; cur += RB * b.ld_out;
+      if (act_keeps_z(b.act)) { b.offZ = cur; cur += RB * b.ld_out; } else b.offZ = -1;
+      if (l >= 1) { b.offD = cur; cur += RB * b.ld_out; } else b.offD = -1;
+    }
+    wp.ldmax = wp.b[0].ld_out;
+    wp.offDa = cur; cur += WTR * wp.b[0].ld_out;
+    wp.offDb = wp.offDa;
+    wp.offScr = cur; cur += wide_scratch_elems(mp);
+    wp.offW = cur; cur += wp.Ppad;
+    wp.offG = cur; cur += wp.Ppad - wp.b[0].pb;
+    cur = (cur + 1) / 2 * 2;
+    wp.offRed = cur; cur += 64 * 2;
+    wp.smem_elems = cur;
+    if ((size_t)cur * 4 <= SMEM_LIMIT) return true;
+  }
+  return false;
 }
 
 static int plan_predict(tbnn_handle* h) {
@@ -273,10 +306,11 @@ extern "C" int tbnn_create(const tbnn_desc* d, tbnn_handle** out) {
   CU(cudaGetDeviceProperties(&prop, d->device));
   h->num_sms = prop.multiProcessorCount;
   if (plan_structure(d, h->mp) || plan_train(h->mp, h->esz)) { delete h; return 1; }
+  h->use_wide = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_WIDE) && plan_wide(h->mp, h->wp);
   if (plan_predict(h)) h->pp_rows = 0;   // predictor unavailable for this network/dtype; tbnn_predict reports it
   const ModelPlan& mp = h->mp;
   const size_t C = h->C, e = h->esz, pp = (size_t)mp.Ppad;
-  h->nblkF = (mp.Ppad + 255) / 256;
+  h->nblkF = (mp.Ppad + 31) / 32;   // enough for both finalize variants
   CU(cudaMalloc(&h->theta_pad, C * pp * e));
   CU(cudaMalloc(&h->theta0_pad, C * pp * e));
   CU(cudaMalloc(&h->mom_pad, C * pp * e));
@@ -309,6 +343,16 @@ extern "C" int tbnn_destroy(tbnn_handle* h) {
 extern "C" int tbnn_num_params(const tbnn_handle* h) { return h ? h->mp.P : -1; }
 extern "C" int tbnn_num_hypers(const tbnn_handle* h) { return h ? h->mp.H : -1; }
 extern "C" int64_t tbnn_launch_count(const tbnn_handle* h) { return h ? h->launches : -1; }
+extern "C" int tbnn_sweep_info(const tbnn_handle* h, int* kernel_kind, int* ctas_per_chain, int* rows_per_tile,
+                               int* smem_bytes) {
+  if (!h) return fail("null handle");
+  const ModelPlan& p = h->use_wide ? h->wp : h->mp;
+  if (kernel_kind) *kernel_kind = h->use_wide ? 1 : 0;
+  if (ctas_per_chain) *ctas_per_chain = h->S;
+  if (rows_per_tile) *rows_per_tile = p.TR;
+  if (smem_bytes) *smem_bytes = (int)((size_t)p.smem_elems * h->esz);
+  return 0;
+}
 
 static int sync_n_total(tbnn_handle* h, cudaStream_t st) {
   h->N_total = h->N;
@@ -324,11 +368,17 @@ static int sync_n_total(tbnn_handle* h, cudaStream_t st) {
 static int after_data(tbnn_handle* h, long long n_rows) {
   if (n_rows <= 0) return fail("n_rows must be positive");
   h->N = n_rows;
-  const long long ntile = (n_rows + h->mp.TR - 1) / h->mp.TR;
-  long long smax = std::max(1, h->num_sms / h->C);
-  smax = std::min(smax, ntile);
-  const long long q = (ntile + smax - 1) / smax;
-  h->S = (int)((ntile + q - 1) / q);
+  if (h->use_wide) {
+    // row-granular balanced split: every CTA gets N/S (+-1) rows, at least 8
+    long long smax = std::max(1, h->num_sms / h->C);
+    h->S = (int)std::max<long long>(1, std::min<long long>(smax, (n_rows + 7) / 8));
+  } else {
+    const long long ntile = (n_rows + h->mp.TR - 1) / h->mp.TR;
+    long long smax = std::max(1, h->num_sms / h->C);
+    smax = std::min(smax, ntile);
+    const long long q = (ntile + smax - 1) / smax;
+    h->S = (int)((ntile + q - 1) / q);
+  }
   const size_t need = (size_t)h->C * h->S * h->mp.Ppad * h->esz;
   if (need > h->partial_cap) {
     if (h->partial) cudaFree(h->partial);
@@ -360,14 +410,25 @@ extern "C" int tbnn_set_data_host(tbnn_handle* h, const void* X, const void* Y, 
   return after_data(h, n_rows);
 }
 
+// the row sweep: wide-first-layer kernel when planned (fp32), else the generic tile engine
+template <typename T>
+static void sweep(tbnn_handle* h, bool backward, cudaStream_t st) {
+  if (h->use_wide) {
+    launch_sweep_wide(h->wp, h->C, h->S, backward, (const float*)h->theta_pad, (const float*)h->X,
+                      (const float*)h->Y, h->N, (float*)h->partial, h->stat_part, st);
+  } else {
+    Launch<T>::partial(h->mp, h->C, h->S, backward, (const T*)h->theta_pad, (const T*)h->X, (const T*)h->Y,
+                       h->N, (T*)h->partial, h->stat_part, st);
+  }
+  h->launches++;
+}
+
 // one likelihood sweep + gradient assembly / leapfrog update
 template <typename T>
 static int eval_step(tbnn_handle* h, const T* hyper, StepCoef cf, double* logp, double* stat_out,
                      cudaStream_t st) {
   const ModelPlan& mp = h->mp;
-  Launch<T>::partial(mp, h->C, h->S, true, (const T*)h->theta_pad, (const T*)h->X, (const T*)h->Y, h->N,
-                     (T*)h->partial, h->stat_part, st);
-  h->launches++;
+  sweep<T>(h, true, st);
   const T* gsum = nullptr;
   if (h->comm) {
     Launch<T>::reduce_partials(mp, h->C, h->S, (const T*)h->partial, h->stat_part, (T*)h->gsum, st);
@@ -530,10 +591,8 @@ static int time_sweep_impl(tbnn_handle* h, const void* theta, int iters, float* 
   for (auto& e : ev) CU(cudaEventCreate(&e));
   for (int i = 0; i < iters; ++i) {
     CU(cudaEventRecord(ev[2 * i], st));
-    Launch<T>::partial(mp, h->C, h->S, true, (const T*)h->theta_pad, (const T*)h->X, (const T*)h->Y, h->N,
-                       (T*)h->partial, h->stat_part, st);
+    sweep<T>(h, true, st);
     CU(cudaEventRecord(ev[2 * i + 1], st));
-    h->launches++;
   }
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
@@ -560,15 +619,34 @@ extern "C" int tbnn_time_sweep(tbnn_handle* h, const void* theta, int iters, flo
                               : time_sweep_impl<double>(h, theta, iters, avg_ms, min_ms, st);
 }
 
+// Developer aid: phase clocks (clock64 of CTA 0) of one wide-sweep launch; clocks[0] = number of marks.
+extern "C" int tbnn_wide_profile(tbnn_handle* h, const void* theta, long long* clocks_host64, void* stream) {
+  CK(check_ready(h));
+  if (!theta || !clocks_host64) return fail("null argument");
+  if (!h->use_wide) return fail("the handle does not use the wide-first-layer sweep");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long* d = nullptr;
+  CU(cudaMalloc(&d, 64 * sizeof(long long)));
+  CU(cudaMemsetAsync(d, 0, 64 * sizeof(long long), st));
+  Launch<float>::pad(h->mp, h->C, (const float*)theta, (float*)h->theta_pad, st);
+  for (int rep = 0; rep < 3; ++rep)   // the last (warm) launch is the one reported
+    launch_sweep_wide(h->wp, h->C, h->S, true, (const float*)h->theta_pad, (const float*)h->X, (const float*)h->Y,
+                      h->N, (float*)h->partial, h->stat_part, st, d);
+  h->launches += 4;
+  CU(cudaMemcpyAsync(clocks_host64, d, 64 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  cudaFree(d);
+  return 0;
+}
+
 // SSE of the current theta (forward-only sweep) for the Gaussian likelihood's hyper term
 template <typename T>
 static int compute_sse(tbnn_handle* h, const void* theta, cudaStream_t st) {
   const ModelPlan& mp = h->mp;
   Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st);
-  Launch<T>::partial(mp, h->C, h->S, false, (const T*)h->theta_pad, (const T*)h->X, (const T*)h->Y, h->N,
-                     (T*)h->partial, h->stat_part, st);
+  sweep<T>(h, false, st);
   k_sum_stat<<<(h->C + 127) / 128, 128, 0, st>>>(h->stat_part, h->S, h->sse_tmp(), h->C);
-  h->launches += 3;
+  h->launches += 2;
   if (h->comm)
     NC(g_nccl.AllReduce(h->sse_tmp(), h->sse_tmp(), (size_t)h->C, 8 /*ncclDouble*/, 0, h->comm, st));
   return 0;

@@ -252,6 +252,105 @@ k_finalize(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ pa
   }
 }
 
+
+// Same contract as k_finalize, for MANY partial vectors (single chain on all SMs): a CTA owns 32
+// consecutive parameters (one 128-byte line of every partial vector) and its 8 warps split the S
+// partials; fixed summation order => deterministic.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_finalize_split(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ partial,
+                 const double* __restrict__ stat_part, const T* __restrict__ hyper, long long Ntot,
+                 T* __restrict__ theta_pad, T* __restrict__ mom_pad, T* __restrict__ grad_pad,
+                 const T* __restrict__ eps_dev, StepCoef cf, double* __restrict__ logp,
+                 double* __restrict__ stat_out, double* __restrict__ prior_part,
+                 unsigned* __restrict__ ticket) {
+  __shared__ double red[40];
+  __shared__ double gs[8][33];
+  __shared__ int is_last;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y, i = blockIdx.x * 32 + tx;
+  const T* hy = hyper + (size_t)c * mp.H;
+  double g = 0.0;
+  if (i < mp.Ppad) {
+    const T* src = partial + (size_t)c * S * mp.Ppad + i;
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+    int s = ty;
+    for (; s + 24 < S; s += 32) {
+      g0 += (double)src[(size_t)s * mp.Ppad];
+      g1 += (double)src[(size_t)(s + 8) * mp.Ppad];
+      g2 += (double)src[(size_t)(s + 16) * mp.Ppad];
+      g3 += (double)src[(size_t)(s + 24) * mp.Ppad];
+    }
+    for (; s < S; s += 8) g0 += (double)src[(size_t)s * mp.Ppad];
+    g = (g0 + g1) + (g2 + g3);
+  }
+  gs[ty][tx] = g;
+  __syncthreads();
+  double sg = 1.0, scale = 1.0;
+  if (mp.lik == LIK_GAUSS) {
+    const double h = (double)hy[mp.lik_h];
+    sg = fmin(fmax(h * h, 1e-8), 1e8);
+    scale = 1.0 / (sg * sg);
+  } else if (mp.lik == LIK_FIXED) {
+    sg = fmin(fmax(mp.fixed_sd, 1e-8), 1e8);
+    scale = 1.0 / (sg * sg);
+  }
+  double pv = 0.0;
+  if (ty == 0 && i < mp.Ppad) {
+    const Elem e = decode_elem(mp, i);
+    const size_t gi = (size_t)c * mp.Ppad + i;
+    if (e.kind) {
+      g = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g += gs[j][tx];
+      const T th = theta_pad[gi];
+      double pg = 0.0;
+      prior_elem<T>(mp, e, hy, (double)th, pv, pg);
+      const T gt = (T)(g * scale + pg);
+      grad_pad[gi] = gt;
+      if (cf.m1 != 0.0 || cf.m2 != 0.0 || cf.m3 != 0.0) {
+        const T eps = eps_dev[c];
+        T p = mom_pad[gi];
+        if (cf.m1 != 0.0) p = p + (T(cf.m1) * eps) * gt;
+        if (cf.m2 != 0.0) p = p - (T(cf.m2) * eps) * gt;
+        mom_pad[gi] = p;
+        if (cf.m3 != 0.0) theta_pad[gi] = th + (T(cf.m3) * eps) * p;
+      }
+    } else {
+      grad_pad[gi] = T(0);
+    }
+  }
+  if (logp == nullptr) return;
+  const double bs = block_sum(pv, red);
+  if (threadIdx.x == 0) {
+    prior_part[(size_t)c * gridDim.x + blockIdx.x] = bs;
+    __threadfence();
+    const unsigned t = atomicAdd(&ticket[c], 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x)
+    acc += __ldcg(&prior_part[(size_t)c * gridDim.x + j]);
+  const double prior = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    double st = 0.0;
+    for (int s = 0; s < S; ++s) st += stat_part[(size_t)c * S + s];
+    double ll;
+    if (mp.lik == LIK_BERN) {
+      ll = st;
+    } else {
+      const double n = (double)Ntot * (double)mp.OUT;
+      ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * 1.8378770664093453);
+    }
+    logp[c] = prior + ll;
+    if (stat_out) stat_out[c] = st;
+    ticket[c] = 0u;
+  }
+}
+
 // ------------------------------------------------------------------ momentum draw
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -364,6 +463,12 @@ void Launch<T>::finalize(const ModelPlan& mp, int C, int S, const T* partial, co
                          const T* gsum, const T* hyper, long long N_total, T* theta_pad, T* mom_pad,
                          T* grad_pad, const T* eps_dev, StepCoef cf, double* logp, double* stat_out,
                          double* prior_part, unsigned* ticket, cudaStream_t st) {
+  if (gsum == nullptr && S >= FINALIZE_SPLIT_MIN_S) {
+    dim3 g2((mp.Ppad + 31) / 32, C);
+    k_finalize_split<T><<<g2, 256, 0, st>>>(mp, S, partial, stat_part, hyper, N_total, theta_pad, mom_pad,
+                                            grad_pad, eps_dev, cf, logp, stat_out, prior_part, ticket);
+    return;
+  }
   dim3 g((mp.Ppad + 255) / 256, C);
   k_finalize<T><<<g, 256, 0, st>>>(mp, S, partial, stat_part, gsum, hyper, N_total, theta_pad, mom_pad,
                                    grad_pad, eps_dev, cf, logp, stat_out, prior_part, ticket);

@@ -10,6 +10,10 @@ namespace tbnn {
 // p = a1*eps*g applied as: p += m1*eps*g ; p -= m2*eps*g ; theta += m3*eps*p   (per chain eps)
 struct StepCoef { double m1, m2, m3; };
 
+// finalize uses the S-split variant (CTA = 32 parameters x 8 S-slices) from this many partials on;
+// prior_part must hold C * ceil(Ppad/32) doubles.
+constexpr int FINALIZE_SPLIT_MIN_S = 16;
+
 template <typename T> struct Launch {
   // flat <-> padded
   static void pad(const ModelPlan& mp, int C, const T* flat, T* padded, cudaStream_t st);
@@ -47,6 +51,14 @@ template <typename T> struct Launch {
                       long long S_total, const T* X, long long M, int rows_per_cta, T* out,
                       T* moments, cudaStream_t st);
 };
+
+// wide-first-layer row sweep (k_wide.cu), fp32 only; `wp` is the wide plan (TR = wide_rows_per_pass()).
+bool wide_supported(const ModelPlan& mp);
+int wide_rows_per_pass();
+int wide_scratch_elems(const ModelPlan& mp);
+void launch_sweep_wide(const ModelPlan& wp, int C, int S, bool backward, const float* theta_pad,
+                       const float* X, const float* Y, long long N, float* partial, double* stat_part,
+                       cudaStream_t st, long long* prof = nullptr);
 
 void launch_adapter_ucb(const float* eGrid, int eNumber, const float* lGrid, int lNumber,
                         const float* prev, int n_hist, const float* Kinv, const float* KinvR, float s,

@@ -37,6 +37,7 @@ struct BlockPlan {
   // smem (per tile) offsets, in elements
   int offS;            // output buffer  S_l = act(z)      [TRp][ld_out]
   int offZ;            // z buffer (only if act_keeps_z)    [TRp][ld_out]  (-1: none)
+  int offD;            // narrow-tail plans only: dz buffer [RB][ld_out] of blocks >= 1 (-1: none)
   int ksplit;          // split-K factor of the forward GEMM
 };
 

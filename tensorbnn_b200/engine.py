@@ -18,7 +18,7 @@ def _stream():
 
 
 class Engine(object):
-    def __init__(self, arch, lik, dtype=torch.float32, chains=1, device=None):
+    def __init__(self, arch, lik, dtype=torch.float32, chains=1, device=None, flags=0):
         if not torch.cuda.is_available():
             raise RuntimeError("tensorbnn_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -30,7 +30,7 @@ class Engine(object):
         code = _lib.F32 if dtype == torch.float32 else _lib.F64
         if dtype not in (torch.float32, torch.float64):
             raise ValueError("dtype must be float32 or float64")
-        desc, self._keep = _lib.make_desc(self.arch, self.lik, code, self.chains, self.device)
+        desc, self._keep = _lib.make_desc(self.arch, self.lik, code, self.chains, self.device, flags)
         h = C.c_void_p()
         _lib.check(self.lib.tbnn_create(C.byref(desc), C.byref(h)))
         self.h = h
@@ -60,6 +60,13 @@ class Engine(object):
     @property
     def launches(self):
         return int(self.lib.tbnn_launch_count(self.h))
+
+    def sweep_info(self):
+        """dict(kernel=..., ctas_per_chain=..., rows_per_tile=..., smem_bytes=...) of the planned row sweep."""
+        k, s, r, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self.lib.tbnn_sweep_info(self.h, C.byref(k), C.byref(s), C.byref(r), C.byref(b)))
+        return {"kernel": ["k_partial", "k_sweep_wide"][k.value], "ctas_per_chain": s.value,
+                "rows_per_tile": r.value, "smem_bytes": b.value}
 
     # ------------------------------------------------------------------ data
     def set_data(self, X, Y):

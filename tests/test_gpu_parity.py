@@ -19,9 +19,9 @@ pytestmark = pytest.mark.gpu
 TOL = {torch.float32: 1e-5, torch.float64: 1e-10}
 
 
-def _engine(arch, lik, dtype, chains=1):
+def _engine(arch, lik, dtype, chains=1, flags=0):
     from tensorbnn_b200.engine import Engine
-    return Engine(arch, lik, dtype=dtype, chains=chains)
+    return Engine(arch, lik, dtype=dtype, chains=chains, flags=flags)
 
 
 ARCHS = {
@@ -36,6 +36,11 @@ ARCHS = {
                ("leakyrelu", 0.3), ("dense", 3, 1), ("sigmoid",)], ("bernoulli",)),
     "c4s": (wl.mlp_arch([32, 128, 128, 128, 1], "dense", "relu"), ("gaussian", 0.1)),
     "wide_out": (wl.mlp_arch([5, 9, 3], "denseGaussian", "tanh"), ("gaussian", 0.5)),
+    # wide first layers (k_wide.cu): slopes in block 0, a single dense layer, the 32-output limit
+    "wide_sq": ([("dense", 128, 12), ("squareprelu", 12), ("dense", 12, 1)], ("gaussian", 0.3)),
+    "wide_single": ([("denseGaussian", 64, 3)], ("gaussian", 0.4)),
+    "wide32": ([("dense", 896, 32), ("tanh",), ("dense", 32, 2)], ("fixed", 0.5)),
+    "wide_prelu": ([("denseGaussian", 200, 7), ("prelu", 7), ("dense", 7, 1), ("sigmoid",)], ("bernoulli",)),
 }
 
 
@@ -71,7 +76,9 @@ def rel(a, b):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("key,N", [("c1a", 11), ("c1b", 11), ("bern", 37), ("c2s", 150), ("sqp", 61),
                                    ("c3s", 200), ("prelu", 29), ("mixed", 45), ("c4s", 70),
-                                   ("wide_out", 33), ("c1a", 1), ("bern", 3), ("c3s", 4096)])
+                                   ("wide_out", 33), ("c1a", 1), ("bern", 3), ("c3s", 4096),
+                                   ("wide_sq", 77), ("wide_single", 40), ("wide32", 19), ("wide_prelu", 333),
+                                   ("c2s", 9), ("c2s", 2500)])
 def test_logp_grad(key, N, dtype):
     arch, lik, X, Y, TH, HY = problem(key, N, chains=2)
     eng = _engine(arch, lik, dtype, chains=2)
@@ -100,6 +107,23 @@ def test_logp_grad_matches_autograd_oracle(dtype):
     lp_ref, g_ref = targets.main_value_and_grad(arch, lik, f64(TH[0]), f64(HY[0]), f64(X), f64(Y))
     assert abs(lp.item() - lp_ref.item()) <= TOL[dtype] * abs(lp_ref.item())
     assert rel(g.cpu().numpy()[0], g_ref.numpy()) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("key,N", [("c2s", 1000), ("wide_sq", 130), ("wide_prelu", 41)])
+def test_wide_sweep_equals_generic_engine(key, N):
+    """The wide-first-layer kernel and the generic tile engine compute the same target (fp32)."""
+    from tensorbnn_b200 import _lib
+    arch, lik, X, Y, TH, HY = problem(key, N, chains=3)
+    out = []
+    for flags in (0, _lib.FLAG_NO_WIDE):
+        eng = _engine(arch, lik, torch.float32, chains=3, flags=flags)
+        eng.set_data(X, Y)
+        assert eng.sweep_info()["kernel"] == ("k_sweep_wide" if flags == 0 else "k_partial")
+        lp, g, st = eng.logp_grad(TH, HY)
+        out.append((lp.cpu().numpy(), g.cpu().numpy(), st.cpu().numpy()))
+    assert np.allclose(out[0][0], out[1][0], rtol=2e-6, atol=0)
+    assert np.allclose(out[0][2], out[1][2], rtol=2e-6, atol=0)
+    assert rel(out[0][1], out[1][1]) <= 5e-6
 
 
 def test_bernoulli_saturation_matches_fp32_oracle():
