@@ -53,7 +53,8 @@ enum { TBNN_F32 = 0, TBNN_F64 = 1 };
 
 /* tbnn_desc.flags: kernel-selection overrides used by the parity tests (results are the same
  * target either way; only the kernel that computes it changes). */
-enum { TBNN_FLAG_NO_WIDE = 1 /* never use the wide-first-layer row sweep */ };
+enum { TBNN_FLAG_NO_WIDE = 1, /* never use the wide-first-layer row sweep */
+       TBNN_FLAG_NO_UMMA = 2  /* never use the tcgen05 (tensor-core) kernels */ };
 
 typedef struct {
   int32_t kind;    /* TBNN_DENSE_* or TBNN_ACT_* */
@@ -162,6 +163,10 @@ int tbnn_adapter_ucb(int device, const float* eGrid, int eNumber, const float* l
  * [3][out][M] = {count, mean, M2} over the S samples (posterior predictive mean / sd). */
 int tbnn_predict(tbnn_handle* h, const void* samples, int64_t S, const void* Xtest, int64_t M,
                  void* out, void* moments, void* stream);
+
+/* Which predictor kernel tbnn_predict uses: 0 = FFMA tile engine (k_predict), 1 = tcgen05 3xTF32
+ * tensor-core sweep (k_predict_umma: fp32, <= 8 inputs, <= 4 outputs, hidden widths <= 80). */
+int tbnn_predict_info(const tbnn_handle* h, int* kernel_kind);
 
 /* Row-sharded sampling (BASELINE config 4): every rank holds rows [r*N/G,(r+1)*N/G) and
  * all-reduces likelihood partials once per gradient evaluation.  unique_id is the 128-byte

@@ -14,9 +14,10 @@ DENSE = {"dense": DENSE_CAUCHY, "denseGaussian": DENSE_GAUSSIAN}
 LIK = {"gaussian": 0, "fixed": 1, "bernoulli": 2}
 F32, F64 = 0, 1
 FLAG_NO_WIDE = 1   # tbnn_desc.flags: never use the wide-first-layer row sweep
+FLAG_NO_UMMA = 2   # tbnn_desc.flags: never use the tcgen05 (tensor-core) kernels
 
 EXPORTS = ["tbnn_last_error", "tbnn_version", "tbnn_create", "tbnn_destroy", "tbnn_num_params",
-           "tbnn_num_hypers", "tbnn_launch_count", "tbnn_sweep_info", "tbnn_wide_profile", "tbnn_set_data", "tbnn_set_data_host",
+           "tbnn_num_hypers", "tbnn_launch_count", "tbnn_sweep_info", "tbnn_wide_profile", "tbnn_predict_info", "tbnn_set_data", "tbnn_set_data_host",
            "tbnn_logp_grad", "tbnn_hyper_logp_grad", "tbnn_trajectory", "tbnn_hmc_step",
            "tbnn_draw_momentum", "tbnn_time_sweep", "tbnn_hyper_step", "tbnn_adapter_ucb", "tbnn_predict", "tbnn_comm_unique_id",
            "tbnn_comm_init"]
@@ -58,6 +59,7 @@ def load():
     lib.tbnn_launch_count.restype = i64
     pi = C.POINTER(C.c_int)
     lib.tbnn_sweep_info.argtypes = [vp, pi, pi, pi, pi]
+    lib.tbnn_predict_info.argtypes = [vp, pi]
     lib.tbnn_wide_profile.argtypes = [vp, vp, C.POINTER(C.c_longlong), vp]
     lib.tbnn_set_data.argtypes = [vp, vp, vp, i64]
     lib.tbnn_set_data_host.argtypes = [vp, vp, vp, i64, vp]

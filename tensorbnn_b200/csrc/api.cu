@@ -67,6 +67,7 @@ struct tbnn_handle {
   ModelPlan mp;        // training plan
   ModelPlan wp;        // wide-first-layer sweep plan (fp32 only)
   bool use_wide = false;
+  bool use_umma_predict = false;   // tcgen05 predictor (fp32, GEMM-shaped hidden layers)
   ModelPlan pp;        // predictor (forward-only) plan
   int pp_rows = 0;     // rows per CTA of the predictor
   // data
@@ -307,6 +308,7 @@ extern "C" int tbnn_create(const tbnn_desc* d, tbnn_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (plan_structure(d, h->mp) || plan_train(h->mp, h->esz)) { delete h; return 1; }
   h->use_wide = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_WIDE) && plan_wide(h->mp, h->wp);
+  h->use_umma_predict = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_UMMA) && predict_umma_supported(h->mp);
   if (plan_predict(h)) h->pp_rows = 0;   // predictor unavailable for this network/dtype; tbnn_predict reports it
   const ModelPlan& mp = h->mp;
   const size_t C = h->C, e = h->esz, pp = (size_t)mp.Ppad;
@@ -343,6 +345,11 @@ extern "C" int tbnn_destroy(tbnn_handle* h) {
 extern "C" int tbnn_num_params(const tbnn_handle* h) { return h ? h->mp.P : -1; }
 extern "C" int tbnn_num_hypers(const tbnn_handle* h) { return h ? h->mp.H : -1; }
 extern "C" int64_t tbnn_launch_count(const tbnn_handle* h) { return h ? h->launches : -1; }
+extern "C" int tbnn_predict_info(const tbnn_handle* h, int* kernel_kind) {
+  if (!h) return fail("null handle");
+  if (kernel_kind) *kernel_kind = h->use_umma_predict ? 1 : 0;
+  return 0;
+}
 extern "C" int tbnn_sweep_info(const tbnn_handle* h, int* kernel_kind, int* ctas_per_chain, int* rows_per_tile,
                                int* smem_bytes) {
   if (!h) return fail("null handle");
@@ -786,9 +793,17 @@ extern "C" int tbnn_predict(tbnn_handle* h, const void* samples, int64_t S, cons
   if (!h || !samples || !Xtest) return fail("null argument");
   if (S < 1 || M < 1) return fail("S and M must be positive");
   if (!out && !moments) return fail("one of out / moments must be given");
-  if (h->pp_rows <= 0) return fail("network too large for the predictor kernel (weights must fit in shared memory)");
   CU(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->use_umma_predict) {
+    if (!launch_predict_umma(h->mp, h->num_sms, (const float*)samples, 0, S, (const float*)Xtest, M, (float*)out,
+                             (float*)moments, st))
+      return fail("internal: tcgen05 predictor plan rejected at launch");
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+  }
+  if (h->pp_rows <= 0) return fail("network too large for the predictor kernel (weights must fit in shared memory)");
   return h->dtype == TBNN_F32 ? predict_impl<float>(h, samples, S, Xtest, M, out, moments, st)
                               : predict_impl<double>(h, samples, S, Xtest, M, out, moments, st);
 }

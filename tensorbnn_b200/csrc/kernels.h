@@ -60,6 +60,11 @@ void launch_sweep_wide(const ModelPlan& wp, int C, int S, bool backward, const f
                        const float* X, const float* Y, long long N, float* partial, double* stat_part,
                        cudaStream_t st, long long* prof = nullptr);
 
+// tcgen05 (3xTF32) posterior-predictive sweep (k_predict_umma.cu), fp32 only; samples are FLAT [S][P].
+bool predict_umma_supported(const ModelPlan& mp);
+bool launch_predict_umma(const ModelPlan& mp, int num_sms, const float* samples, long long s0, long long S_chunk,
+                         const float* X, long long M, float* out, float* moments, cudaStream_t st);
+
 void launch_adapter_ucb(const float* eGrid, int eNumber, const float* lGrid, int lNumber,
                         const float* prev, int n_hist, const float* Kinv, const float* KinvR, float s,
                         float p, float rootbeta, float el, float eu, float Ll, float Lu,

@@ -68,6 +68,11 @@ class Engine(object):
         return {"kernel": ["k_partial", "k_sweep_wide"][k.value], "ctas_per_chain": s.value,
                 "rows_per_tile": r.value, "smem_bytes": b.value}
 
+    def predict_kernel(self):
+        k = C.c_int()
+        _lib.check(self.lib.tbnn_predict_info(self.h, C.byref(k)))
+        return ["k_predict", "k_predict_umma"][k.value]
+
     # ------------------------------------------------------------------ data
     def set_data(self, X, Y):
         X = self.tensor(X)

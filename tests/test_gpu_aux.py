@@ -124,6 +124,11 @@ def test_adapter_first_maximum_tie_break():
     assert e == float(eGrid[0]) and L == float(lGrid[0]) and ucb == 0.0
 
 
+def _engine_flags(arch, lik, dtype, flags):
+    from tensorbnn_b200.engine import Engine
+    return Engine(arch, lik, dtype=dtype, flags=flags)
+
+
 # ---------------------------------------------------------------------------- predictor
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("arch", [wl.mlp_arch([1, 64, 64, 64, 1], "dense", "squareprelu"),
@@ -161,6 +166,60 @@ def test_predict_moments_only_many_samples():
     samples = th0[None, :] + 0.05 * rng.normal(size=(S, th0.size))
     X = np.linspace(-4, 4, M)[:, None]
     eng = _engine(arch, lik, torch.float32)
+    _, mom = eng.predict(samples, X, want_out=False, want_moments=True)
+    out, _ = eng.predict(samples, X, want_out=True, want_moments=False)
+    out = out.cpu().numpy().astype(np.float64)
+    mom = mom.cpu().numpy()
+    assert np.abs(mom[1] - out.mean(axis=0)).max() <= 1e-5 * max(1.0, np.abs(out).max())
+    assert np.abs(mom[2] / S - out.var(axis=0)).max() <= 1e-4 * out.var(axis=0).max() + 1e-9
+
+
+# ---------------------------------------------------------------------------- tcgen05 predictor
+UMMA_ARCHS = [wl.mlp_arch([1, 64, 64, 64, 1], "dense", "squareprelu"),
+              wl.mlp_arch([3, 40, 24, 2], "denseGaussian", "tanh"),
+              wl.mlp_arch([2, 32, 48, 16, 1], "dense", "relu", "sigmoid"),
+              [("dense", 8, 80), ("elu",), ("dense", 80, 72), ("prelu", 72), ("dense", 72, 4)]]
+
+
+@pytest.mark.parametrize("arch", UMMA_ARCHS)
+@pytest.mark.parametrize("S,M", [(5, 700), (3, 128), (2, 1)])
+def test_predict_tensor_core_kernel_matches_oracle(arch, S, M):
+    """k_predict_umma (tcgen05, 3xTF32 from TMEM) vs the fp64 oracle and vs the FFMA predictor."""
+    from tensorbnn_b200 import _lib
+    lik = ("fixed", 0.1)
+    rng = np.random.default_rng(2)
+    th0 = wl.init_theta(arch, seed=3)
+    samples = th0[None, :] + 0.05 * rng.normal(size=(S, th0.size))
+    D = arch[0][1]
+    X = rng.normal(size=(M, D))
+    eng = _engine(arch, lik, torch.float32)
+    assert eng.predict_kernel() == "k_predict_umma"
+    out, mom = eng.predict(samples, X, want_out=True, want_moments=True)
+    ffma = _engine_flags(arch, lik, torch.float32, _lib.FLAG_NO_UMMA)
+    assert ffma.predict_kernel() == "k_predict"
+    out2, mom2 = ffma.predict(samples, X, want_out=True, want_moments=True)
+    r = lambda a: torch.tensor(np.asarray(a).astype(np.float32).astype(np.float64))
+    ref = np.stack([targets.forward(arch, targets.unflatten_theta(arch, r(samples[s])), r(X)).numpy()
+                    for s in range(S)])
+    out, out2, mom, mom2 = out.cpu().numpy(), out2.cpu().numpy(), mom.cpu().numpy(), mom2.cpu().numpy()
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(out - ref).max() <= 2e-5 * scale
+    assert np.abs(out - out2).max() <= 2e-5 * scale
+    assert np.all(mom[0] == S)
+    assert np.abs(mom[1] - mom2[1]).max() <= 2e-5 * scale
+    assert np.abs(mom[2] - mom2[2]).max() <= 1e-4 * max(1e-12, np.abs(mom2[2]).max()) + 1e-6
+
+
+def test_predict_tensor_core_moments_accumulate_across_calls():
+    """The fused (count, mean, M2) mode over many samples equals the materialised outputs' moments."""
+    arch = wl.mlp_arch([1, 64, 64, 64, 1], "dense", "squareprelu")
+    rng = np.random.default_rng(5)
+    th0 = wl.init_theta(arch, seed=9, slope=0.1 ** 0.5)
+    S, M = 64, 3000
+    samples = th0[None, :] + 0.05 * rng.normal(size=(S, th0.size))
+    X = np.linspace(-4, 4, M)[:, None]
+    eng = _engine(arch, ("gaussian", 0.1), torch.float32)
+    assert eng.predict_kernel() == "k_predict_umma"
     _, mom = eng.predict(samples, X, want_out=False, want_moments=True)
     out, _ = eng.predict(samples, X, want_out=True, want_moments=False)
     out = out.cpu().numpy().astype(np.float64)
