@@ -53,8 +53,9 @@ enum { TBNN_F32 = 0, TBNN_F64 = 1 };
 
 /* tbnn_desc.flags: kernel-selection overrides used by the parity tests (results are the same
  * target either way; only the kernel that computes it changes). */
-enum { TBNN_FLAG_NO_WIDE = 1, /* never use the wide-first-layer row sweep */
-       TBNN_FLAG_NO_UMMA = 2  /* never use the tcgen05 (tensor-core) kernels */ };
+enum { TBNN_FLAG_NO_WIDE = 1,  /* never use the wide-first-layer row sweeps */
+       TBNN_FLAG_NO_UMMA = 2,  /* never use the tcgen05 (tensor-core) kernels */
+       TBNN_FLAG_NO_WIDE2 = 4  /* use the phase-serial wide sweep instead of the warp-specialised one */ };
 
 typedef struct {
   int32_t kind;    /* TBNN_DENSE_* or TBNN_ACT_* */
@@ -86,7 +87,8 @@ int tbnn_num_hypers(const tbnn_handle* h);  /* H */
 int64_t tbnn_launch_count(const tbnn_handle* h);
 
 /* Which row-sweep kernel the handle planned: kernel_kind 0 = generic tile engine (k_partial),
- * 1 = wide-first-layer FFMA sweep (k_sweep_wide); CTAs per chain (valid after set_data), rows per
+ * 1 = wide-first-layer FFMA sweep (k_sweep_wide), 2 = warp-specialised wide sweep (k_sweep_wide2; forward-only
+ * sweeps still use kind 1); CTAs per chain (valid after set_data), rows per
  * tile / pass, dynamic shared memory per CTA.  Any out pointer may be NULL. */
 int tbnn_sweep_info(const tbnn_handle* h, int* kernel_kind, int* ctas_per_chain, int* rows_per_tile,
                     int* smem_bytes);

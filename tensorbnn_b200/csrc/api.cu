@@ -66,7 +66,9 @@ struct tbnn_handle {
   size_t esz = 4;
   ModelPlan mp;        // training plan
   ModelPlan wp;        // wide-first-layer sweep plan (fp32 only)
+  ModelPlan w2;        // warp-specialised wide sweep plan (fp32, forward + backward)
   bool use_wide = false;
+  bool use_wide2 = false;
   bool use_umma_predict = false;   // tcgen05 predictor (fp32, GEMM-shaped hidden layers)
   ModelPlan pp;        // predictor (forward-only) plan
   int pp_rows = 0;     // rows per CTA of the predictor
@@ -308,6 +310,7 @@ extern "C" int tbnn_create(const tbnn_desc* d, tbnn_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (plan_structure(d, h->mp) || plan_train(h->mp, h->esz)) { delete h; return 1; }
   h->use_wide = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_WIDE) && plan_wide(h->mp, h->wp);
+  h->use_wide2 = h->use_wide && !(d->flags & TBNN_FLAG_NO_WIDE2) && plan_wide2(h->mp, h->w2, SMEM_LIMIT);
   h->use_umma_predict = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_UMMA) && predict_umma_supported(h->mp);
   if (plan_predict(h)) h->pp_rows = 0;   // predictor unavailable for this network/dtype; tbnn_predict reports it
   const ModelPlan& mp = h->mp;
@@ -353,8 +356,8 @@ extern "C" int tbnn_predict_info(const tbnn_handle* h, int* kernel_kind) {
 extern "C" int tbnn_sweep_info(const tbnn_handle* h, int* kernel_kind, int* ctas_per_chain, int* rows_per_tile,
                                int* smem_bytes) {
   if (!h) return fail("null handle");
-  const ModelPlan& p = h->use_wide ? h->wp : h->mp;
-  if (kernel_kind) *kernel_kind = h->use_wide ? 1 : 0;
+  const ModelPlan& p = h->use_wide2 ? h->w2 : (h->use_wide ? h->wp : h->mp);
+  if (kernel_kind) *kernel_kind = h->use_wide2 ? 2 : (h->use_wide ? 1 : 0);
   if (ctas_per_chain) *ctas_per_chain = h->S;
   if (rows_per_tile) *rows_per_tile = p.TR;
   if (smem_bytes) *smem_bytes = (int)((size_t)p.smem_elems * h->esz);
@@ -420,7 +423,10 @@ extern "C" int tbnn_set_data_host(tbnn_handle* h, const void* X, const void* Y, 
 // the row sweep: wide-first-layer kernel when planned (fp32), else the generic tile engine
 template <typename T>
 static void sweep(tbnn_handle* h, bool backward, cudaStream_t st) {
-  if (h->use_wide) {
+  if (h->use_wide2 && backward) {
+    launch_sweep_wide2(h->w2, h->C, h->S, (const float*)h->theta_pad, (const float*)h->X, (const float*)h->Y, h->N,
+                       (float*)h->partial, h->stat_part, st);
+  } else if (h->use_wide) {
     launch_sweep_wide(h->wp, h->C, h->S, backward, (const float*)h->theta_pad, (const float*)h->X,
                       (const float*)h->Y, h->N, (float*)h->partial, h->stat_part, st);
   } else {

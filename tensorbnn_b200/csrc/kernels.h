@@ -60,6 +60,12 @@ void launch_sweep_wide(const ModelPlan& wp, int C, int S, bool backward, const f
                        const float* X, const float* Y, long long N, float* partial, double* stat_part,
                        cudaStream_t st, long long* prof = nullptr);
 
+// warp-specialised wide-first-layer sweep (k_wide2.cu), fp32, forward + backward only; `wp` from plan_wide2.
+bool wide2_supported(const ModelPlan& mp);
+bool plan_wide2(const ModelPlan& mp, ModelPlan& wp, size_t smem_limit);
+void launch_sweep_wide2(const ModelPlan& wp, int C, int S, const float* theta_pad, const float* X,
+                        const float* Y, long long N, float* partial, double* stat_part, cudaStream_t st);
+
 // tcgen05 (3xTF32) posterior-predictive sweep (k_predict_umma.cu), fp32 only; samples are FLAT [S][P].
 bool predict_umma_supported(const ModelPlan& mp);
 bool launch_predict_umma(const ModelPlan& mp, int num_sms, const float* samples, long long s0, long long S_chunk,

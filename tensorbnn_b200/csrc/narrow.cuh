@@ -167,12 +167,14 @@ __device__ __forceinline__ T narrow_row(const ModelPlan& mp, const T* Wp, T* sm,
 
 // Gradient accumulation of blocks 1..nb-1 over the first `nrows` rows of the batch buffers:
 //   G.W_l += dZ_l^T S_{l-1},  G.b_l += colsum dZ_l,  slope gradients from the c values left in Z_l.
-// Every (l, o, k) is owned by exactly one thread.  Caller synchronises the CTA before and after.
+// Every (l, o, k) is owned by exactly one of the `nthr` cooperating threads (tid = 0..nthr-1); the caller
+// synchronises them before and after.
 template <typename T>
-__device__ __forceinline__ void narrow_accum(const ModelPlan& mp, const T* Wp, T* G, const T* sm, int nrows) {
+__device__ __forceinline__ void narrow_accum(const ModelPlan& mp, const T* Wp, T* G, const T* sm, int nrows,
+                                             int tid, int nthr) {
   int total = 0;
   for (int l = 1; l < mp.nb; ++l) total += (mp.b[l].out_p >> 2) * (mp.b[l].in_p >> 2);
-  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+  for (int t = tid; t < total; t += nthr) {
     int l = 1, u = t;
     for (; l < mp.nb; ++l) {
       const int n = (mp.b[l].out_p >> 2) * (mp.b[l].in_p >> 2);
@@ -212,7 +214,7 @@ __device__ __forceinline__ void narrow_accum(const ModelPlan& mp, const T* Wp, T
   // column sums, handed out from the top of the CTA so they overlap with the tiles above
   int ncol = 0;
   for (int l = 1; l < mp.nb; ++l) ncol += mp.b[l].out_p * (act_has_slopes(mp.b[l].act) ? 2 : 1);
-  for (int t = (int)blockDim.x - 1 - (int)threadIdx.x; t < ncol; t += blockDim.x) {
+  for (int t = nthr - 1 - tid; t < ncol; t += nthr) {
     int l = 1, u = t;
     for (; l < mp.nb; ++l) {
       const int n = mp.b[l].out_p * (act_has_slopes(mp.b[l].act) ? 2 : 1);
@@ -235,6 +237,11 @@ __device__ __forceinline__ void narrow_accum(const ModelPlan& mp, const T* Wp, T
       G[b.pb + o] += s;
     }
   }
+}
+
+template <typename T>
+__device__ __forceinline__ void narrow_accum(const ModelPlan& mp, const T* Wp, T* G, const T* sm, int nrows) {
+  narrow_accum<T>(mp, Wp, G, sm, nrows, (int)threadIdx.x, (int)blockDim.x);
 }
 
 }  // namespace tbnn

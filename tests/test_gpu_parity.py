@@ -109,21 +109,49 @@ def test_logp_grad_matches_autograd_oracle(dtype):
     assert rel(g.cpu().numpy()[0], g_ref.numpy()) <= TOL[dtype]
 
 
-@pytest.mark.parametrize("key,N", [("c2s", 1000), ("wide_sq", 130), ("wide_prelu", 41)])
-def test_wide_sweep_equals_generic_engine(key, N):
-    """The wide-first-layer kernel and the generic tile engine compute the same target (fp32)."""
+@pytest.mark.parametrize("key,N,chains", [("c2s", 1000, 3), ("wide_sq", 130, 3), ("wide_prelu", 41, 3),
+                                          ("c2s", 9600, 1), ("c2s", 7, 2), ("wide_single", 333, 2),
+                                          ("wide32", 97, 2), ("wide_sq", 5000, 1)])
+def test_wide_sweeps_equal_generic_engine(key, N, chains):
+    """The wide-first-layer kernels (warp-specialised k_sweep_wide2, phase-serial k_sweep_wide) and the generic
+    tile engine compute the same target (fp32): log-posterior, gradient, likelihood statistic."""
     from tensorbnn_b200 import _lib
-    arch, lik, X, Y, TH, HY = problem(key, N, chains=3)
-    out = []
-    for flags in (0, _lib.FLAG_NO_WIDE):
-        eng = _engine(arch, lik, torch.float32, chains=3, flags=flags)
+    arch, lik, X, Y, TH, HY = problem(key, N, chains=chains)
+    out = {}
+    for name, flags in (("default", 0), ("serial", _lib.FLAG_NO_WIDE2), ("generic", _lib.FLAG_NO_WIDE)):
+        eng = _engine(arch, lik, torch.float32, chains=chains, flags=flags)
         eng.set_data(X, Y)
-        assert eng.sweep_info()["kernel"] == ("k_sweep_wide" if flags == 0 else "k_partial")
+        kern = eng.sweep_info()["kernel"]
+        if name == "generic":
+            assert kern == "k_partial"
+        elif key == "wide32":
+            assert kern == "k_partial"          # 896 x 32 weights + X tiles exceed shared memory: generic engine
+        elif name == "serial":
+            assert kern == "k_sweep_wide"
+        else:
+            assert kern == "k_sweep_wide2"
         lp, g, st = eng.logp_grad(TH, HY)
-        out.append((lp.cpu().numpy(), g.cpu().numpy(), st.cpu().numpy()))
-    assert np.allclose(out[0][0], out[1][0], rtol=2e-6, atol=0)
-    assert np.allclose(out[0][2], out[1][2], rtol=2e-6, atol=0)
-    assert rel(out[0][1], out[1][1]) <= 5e-6
+        out[name] = (lp.cpu().numpy(), g.cpu().numpy(), st.cpu().numpy())
+    for name in ("default", "serial"):
+        assert np.allclose(out[name][0], out["generic"][0], rtol=2e-6, atol=0), name
+        assert np.allclose(out[name][2], out["generic"][2], rtol=2e-6, atol=0), name
+        assert rel(out[name][1], out["generic"][1]) <= 5e-6, name
+
+
+def test_wide_sweep_is_deterministic_and_matches_oracle():
+    """Run-to-run bit-identical results (fixed summation order) and 1e-5 agreement with the fp64 oracle at the
+    C2 shape (9,600 x 784, 784-20-20-1, Bernoulli)."""
+    arch, lik, X, Y, TH, HY = problem("c2s", 9600)
+    eng = _engine(arch, lik, torch.float32)
+    eng.set_data(X, Y)
+    assert eng.sweep_info()["kernel"] == "k_sweep_wide2"
+    lp1, g1, _ = eng.logp_grad(TH, HY)
+    lp2, g2, _ = eng.logp_grad(TH, HY)
+    assert torch.equal(lp1, lp2) and torch.equal(g1, g2)
+    r32 = lambda a: np.asarray(a).astype(np.float32).astype(np.float64)
+    lp_ref, g_ref = analytic.main_value_and_grad(arch, lik, r32(TH[0]), r32(HY[0]), r32(X), r32(Y))
+    assert abs(lp1.item() - lp_ref) <= 1e-5 * abs(lp_ref)
+    assert rel(g1.cpu().numpy()[0], g_ref) <= 1e-5
 
 
 def test_bernoulli_saturation_matches_fp32_oracle():
