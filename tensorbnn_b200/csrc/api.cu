@@ -82,6 +82,7 @@ struct tbnn_handle {
   int S = 1;
   // workspace
   void *theta_pad = nullptr, *theta0_pad = nullptr, *mom_pad = nullptr, *grad_pad = nullptr;
+  void* w1p = nullptr;   // pair-interleaved W_1 copy of every chain (warp-specialised wide sweep)
   void *partial = nullptr, *gsum = nullptr, *eps_dev = nullptr, *flat_tmp = nullptr, *small_T = nullptr;
   double *stat_part = nullptr, *prior_part = nullptr, *dbl = nullptr;  // dbl: [8][C] doubles
   unsigned* ticket = nullptr;
@@ -316,6 +317,7 @@ extern "C" int tbnn_create(const tbnn_desc* d, tbnn_handle** out) {
   const ModelPlan& mp = h->mp;
   const size_t C = h->C, e = h->esz, pp = (size_t)mp.Ppad;
   h->nblkF = (mp.Ppad + 31) / 32;   // enough for both finalize variants
+  if (h->use_wide2) CU(cudaMalloc(&h->w1p, C * (size_t)w1p_elems(h->mp) * sizeof(float)));
   CU(cudaMalloc(&h->theta_pad, C * pp * e));
   CU(cudaMalloc(&h->theta0_pad, C * pp * e));
   CU(cudaMalloc(&h->mom_pad, C * pp * e));
@@ -338,7 +340,7 @@ extern "C" int tbnn_destroy(tbnn_handle* h) {
   cudaSetDevice(h->device);
   void* ptrs[] = {h->theta_pad, h->theta0_pad, h->mom_pad, h->grad_pad, h->gsum, h->eps_dev, h->flat_tmp,
                   h->small_T, h->prior_part, h->dbl, h->ticket, h->partial, h->stat_part, h->X_own,
-                  h->Y_own, h->pred_ws};
+                  h->Y_own, h->pred_ws, h->w1p};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   delete h;
@@ -424,8 +426,8 @@ extern "C" int tbnn_set_data_host(tbnn_handle* h, const void* X, const void* Y, 
 template <typename T>
 static void sweep(tbnn_handle* h, bool backward, cudaStream_t st) {
   if (h->use_wide2 && backward) {
-    launch_sweep_wide2(h->w2, h->C, h->S, (const float*)h->theta_pad, (const float*)h->X, (const float*)h->Y, h->N,
-                       (float*)h->partial, h->stat_part, st);
+    launch_sweep_wide2(h->w2, h->C, h->S, (const float*)h->theta_pad, (const float*)h->w1p, (const float*)h->X,
+                       (const float*)h->Y, h->N, (float*)h->partial, h->stat_part, st);
   } else if (h->use_wide) {
     launch_sweep_wide(h->wp, h->C, h->S, backward, (const float*)h->theta_pad, (const float*)h->X,
                       (const float*)h->Y, h->N, (float*)h->partial, h->stat_part, st);
@@ -452,7 +454,7 @@ static int eval_step(tbnn_handle* h, const T* hyper, StepCoef cf, double* logp, 
   }
   Launch<T>::finalize(mp, h->C, h->S, (const T*)h->partial, h->stat_part, gsum, hyper, h->N_total,
                       (T*)h->theta_pad, (T*)h->mom_pad, (T*)h->grad_pad, (const T*)h->eps_dev, cf, logp,
-                      stat_out, h->prior_part, h->ticket, st);
+                      stat_out, h->prior_part, h->ticket, st, (T*)h->w1p);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -485,7 +487,7 @@ template <typename T>
 static int logp_grad_impl(tbnn_handle* h, const void* theta, const void* hyper, void* logp, void* grad,
                           void* lik_stat, cudaStream_t st) {
   const ModelPlan& mp = h->mp;
-  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st);
+  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st, (T*)h->w1p);
   h->launches++;
   CK(eval_step<T>(h, (const T*)hyper, StepCoef{0, 0, 0}, h->logp1(), h->stat1(), st));
   if (grad) { Launch<T>::unpad(mp, h->C, (const T*)h->grad_pad, (T*)grad, st); h->launches++; }
@@ -519,7 +521,7 @@ static int trajectory_impl(tbnn_handle* h, const void* theta, const void* hyper,
                            void* grad_out, cudaStream_t st) {
   const ModelPlan& mp = h->mp;
   CK(upload_eps<T>(h, eps_host, st));
-  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st);
+  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st, (T*)h->w1p);
   Launch<T>::pad(mp, h->C, (const T*)momentum, (T*)h->mom_pad, st);
   h->launches += 2;
   CK(leapfrog_impl<T>(h, (const T*)hyper, L, nullptr, nullptr, h->logp1(), h->stat1(), st));
@@ -550,7 +552,7 @@ static int hmc_step_impl(tbnn_handle* h, void* theta, const void* hyper, uint64_
   const ModelPlan& mp = h->mp;
   const size_t bytes = (size_t)h->C * mp.Ppad * sizeof(T);
   CK(upload_eps<T>(h, eps_host, st));
-  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st);
+  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st, (T*)h->w1p);
   CU(cudaMemcpyAsync(h->theta0_pad, h->theta_pad, bytes, cudaMemcpyDeviceToDevice, st));
   Launch<T>::momentum(mp, h->C, seed, counter, (const T*)momentum_in, (T*)h->mom_pad, h->ke0(), st);
   h->launches += 2;
@@ -598,7 +600,7 @@ template <typename T>
 static int time_sweep_impl(tbnn_handle* h, const void* theta, int iters, float* avg_ms, float* min_ms,
                            cudaStream_t st) {
   const ModelPlan& mp = h->mp;
-  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st);
+  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st, (T*)h->w1p);
   h->launches++;
   std::vector<cudaEvent_t> ev(2 * iters);
   for (auto& e : ev) CU(cudaEventCreate(&e));
@@ -641,7 +643,7 @@ extern "C" int tbnn_wide_profile(tbnn_handle* h, const void* theta, long long* c
   long long* d = nullptr;
   CU(cudaMalloc(&d, 64 * sizeof(long long)));
   CU(cudaMemsetAsync(d, 0, 64 * sizeof(long long), st));
-  Launch<float>::pad(h->mp, h->C, (const float*)theta, (float*)h->theta_pad, st);
+  Launch<float>::pad(h->mp, h->C, (const float*)theta, (float*)h->theta_pad, st, (float*)h->w1p);
   for (int rep = 0; rep < 3; ++rep)   // the last (warm) launch is the one reported
     launch_sweep_wide(h->wp, h->C, h->S, true, (const float*)h->theta_pad, (const float*)h->X, (const float*)h->Y,
                       h->N, (float*)h->partial, h->stat_part, st, d);
@@ -656,7 +658,7 @@ extern "C" int tbnn_wide_profile(tbnn_handle* h, const void* theta, long long* c
 template <typename T>
 static int compute_sse(tbnn_handle* h, const void* theta, cudaStream_t st) {
   const ModelPlan& mp = h->mp;
-  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st);
+  Launch<T>::pad(mp, h->C, (const T*)theta, (T*)h->theta_pad, st, (T*)h->w1p);
   sweep<T>(h, false, st);
   k_sum_stat<<<(h->C + 127) / 128, 128, 0, st>>>(h->stat_part, h->S, h->sse_tmp(), h->C);
   h->launches += 2;

@@ -36,13 +36,29 @@ __device__ __forceinline__ Elem decode_elem(const ModelPlan& mp, int i) {
   return e;
 }
 
+// Index of padded element i inside the pair-interleaved copy of W_1 that the warp-specialised wide sweep
+// reads (k_wide2.cu: [k quad][output pair][k in quad][2], w1p_quad_stride() floats per k quad); -1 if i is
+// not an element of W_1.
+__device__ __forceinline__ int w1p_index(const ModelPlan& mp, int i) {
+  const BlockPlan& b = mp.b[0];
+  if (i >= b.pb) return -1;
+  const int o = i / b.ld_in, k = i - o * b.ld_in;
+  if (k >= b.in_p) return -1;
+  return (k >> 2) * w1p_quad_stride(b.out_p) + (o >> 1) * 8 + (k & 3) * 2 + (o & 1);
+}
+
 template <typename T>
 __global__ void k_pad(const __grid_constant__ ModelPlan mp, const T* __restrict__ flat,
-                      T* __restrict__ padded) {
+                      T* __restrict__ padded, T* __restrict__ w1p) {
   const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= mp.Ppad) return;
   const Elem e = decode_elem(mp, i);
-  padded[(size_t)c * mp.Ppad + i] = e.kind ? flat[(size_t)c * mp.P + e.flat] : T(0);
+  const T v = e.kind ? flat[(size_t)c * mp.P + e.flat] : T(0);
+  padded[(size_t)c * mp.Ppad + i] = v;
+  if (w1p) {
+    const int q = w1p_index(mp, i);
+    if (q >= 0) w1p[(size_t)c * w1p_elems(mp) + q] = v;
+  }
 }
 template <typename T>
 __global__ void k_unpad(const __grid_constant__ ModelPlan mp, const T* __restrict__ padded,
@@ -177,7 +193,7 @@ k_finalize(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ pa
            const T* __restrict__ hyper, long long Ntot, T* __restrict__ theta_pad,
            T* __restrict__ mom_pad, T* __restrict__ grad_pad, const T* __restrict__ eps_dev,
            StepCoef cf, double* __restrict__ logp, double* __restrict__ stat_out,
-           double* __restrict__ prior_part, unsigned* __restrict__ ticket) {
+           double* __restrict__ prior_part, unsigned* __restrict__ ticket, T* __restrict__ w1p) {
   __shared__ double red[40];
   __shared__ int is_last;
   const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,7 +230,14 @@ k_finalize(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ pa
         if (cf.m1 != 0.0) p = p + (T(cf.m1) * eps) * gt;
         if (cf.m2 != 0.0) p = p - (T(cf.m2) * eps) * gt;
         mom_pad[gi] = p;
-        if (cf.m3 != 0.0) theta_pad[gi] = th + (T(cf.m3) * eps) * p;
+        if (cf.m3 != 0.0) {
+          const T tn = th + (T(cf.m3) * eps) * p;
+          theta_pad[gi] = tn;
+          if (w1p) {
+            const int q = w1p_index(mp, i);
+            if (q >= 0) w1p[(size_t)c * w1p_elems(mp) + q] = tn;
+          }
+        }
       }
     } else {
       grad_pad[gi] = T(0);
@@ -263,7 +286,7 @@ k_finalize_split(const __grid_constant__ ModelPlan mp, int S, const T* __restric
                  T* __restrict__ theta_pad, T* __restrict__ mom_pad, T* __restrict__ grad_pad,
                  const T* __restrict__ eps_dev, StepCoef cf, double* __restrict__ logp,
                  double* __restrict__ stat_out, double* __restrict__ prior_part,
-                 unsigned* __restrict__ ticket) {
+                 unsigned* __restrict__ ticket, T* __restrict__ w1p) {
   __shared__ double red[40];
   __shared__ double gs[8][33];
   __shared__ int is_last;
@@ -314,7 +337,14 @@ k_finalize_split(const __grid_constant__ ModelPlan mp, int S, const T* __restric
         if (cf.m1 != 0.0) p = p + (T(cf.m1) * eps) * gt;
         if (cf.m2 != 0.0) p = p - (T(cf.m2) * eps) * gt;
         mom_pad[gi] = p;
-        if (cf.m3 != 0.0) theta_pad[gi] = th + (T(cf.m3) * eps) * p;
+        if (cf.m3 != 0.0) {
+          const T tn = th + (T(cf.m3) * eps) * p;
+          theta_pad[gi] = tn;
+          if (w1p) {
+            const int q = w1p_index(mp, i);
+            if (q >= 0) w1p[(size_t)c * w1p_elems(mp) + q] = tn;
+          }
+        }
       }
     } else {
       grad_pad[gi] = T(0);
@@ -429,9 +459,9 @@ k_mh(const __grid_constant__ ModelPlan mp, uint64_t seed, uint64_t call, const T
 
 // ------------------------------------------------------------------ launchers
 template <typename T>
-void Launch<T>::pad(const ModelPlan& mp, int C, const T* flat, T* padded, cudaStream_t st) {
+void Launch<T>::pad(const ModelPlan& mp, int C, const T* flat, T* padded, cudaStream_t st, T* w1p) {
   dim3 g((mp.Ppad + 255) / 256, C);
-  k_pad<T><<<g, 256, 0, st>>>(mp, flat, padded);
+  k_pad<T><<<g, 256, 0, st>>>(mp, flat, padded, w1p);
 }
 template <typename T>
 void Launch<T>::unpad(const ModelPlan& mp, int C, const T* padded, T* flat, cudaStream_t st) {
@@ -462,16 +492,16 @@ template <typename T>
 void Launch<T>::finalize(const ModelPlan& mp, int C, int S, const T* partial, const double* stat_part,
                          const T* gsum, const T* hyper, long long N_total, T* theta_pad, T* mom_pad,
                          T* grad_pad, const T* eps_dev, StepCoef cf, double* logp, double* stat_out,
-                         double* prior_part, unsigned* ticket, cudaStream_t st) {
+                         double* prior_part, unsigned* ticket, cudaStream_t st, T* w1p) {
   if (gsum == nullptr && S >= FINALIZE_SPLIT_MIN_S) {
     dim3 g2((mp.Ppad + 31) / 32, C);
     k_finalize_split<T><<<g2, 256, 0, st>>>(mp, S, partial, stat_part, hyper, N_total, theta_pad, mom_pad,
-                                            grad_pad, eps_dev, cf, logp, stat_out, prior_part, ticket);
+                                            grad_pad, eps_dev, cf, logp, stat_out, prior_part, ticket, w1p);
     return;
   }
   dim3 g((mp.Ppad + 255) / 256, C);
   k_finalize<T><<<g, 256, 0, st>>>(mp, S, partial, stat_part, gsum, hyper, N_total, theta_pad, mom_pad,
-                                   grad_pad, eps_dev, cf, logp, stat_out, prior_part, ticket);
+                                   grad_pad, eps_dev, cf, logp, stat_out, prior_part, ticket, w1p);
 }
 template <typename T>
 void Launch<T>::momentum(const ModelPlan& mp, int C, uint64_t seed, uint64_t call,

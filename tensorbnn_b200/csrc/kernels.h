@@ -16,7 +16,8 @@ constexpr int FINALIZE_SPLIT_MIN_S = 16;
 
 template <typename T> struct Launch {
   // flat <-> padded
-  static void pad(const ModelPlan& mp, int C, const T* flat, T* padded, cudaStream_t st);
+  // w1p (optional): pair-interleaved copy of W_1 kept in step with `padded` (k_wide2.cu)
+  static void pad(const ModelPlan& mp, int C, const T* flat, T* padded, cudaStream_t st, T* w1p = nullptr);
   static void unpad(const ModelPlan& mp, int C, const T* padded, T* flat, cudaStream_t st);
   // likelihood partial gradients: grid (S, C)
   static void partial(const ModelPlan& mp, int C, int S, bool backward, const T* theta_pad,
@@ -30,7 +31,7 @@ template <typename T> struct Launch {
   static void finalize(const ModelPlan& mp, int C, int S, const T* partial, const double* stat_part,
                        const T* gsum, const T* hyper, long long N_total, T* theta_pad, T* mom_pad,
                        T* grad_pad, const T* eps_dev, StepCoef cf, double* logp, double* stat_out,
-                       double* prior_part, unsigned* ticket, cudaStream_t st);
+                       double* prior_part, unsigned* ticket, cudaStream_t st, T* w1p = nullptr);
   // momentum ~ N(0, I) (Philox) or copy of injected flat momentum; ke[c] = 0.5*sum p^2
   static void momentum(const ModelPlan& mp, int C, uint64_t seed, uint64_t call, const T* injected_flat,
                        T* mom_pad, double* ke, cudaStream_t st);
@@ -61,10 +62,15 @@ void launch_sweep_wide(const ModelPlan& wp, int C, int S, bool backward, const f
                        cudaStream_t st, long long* prof = nullptr);
 
 // warp-specialised wide-first-layer sweep (k_wide2.cu), fp32, forward + backward only; `wp` from plan_wide2.
+// It reads W_1 from a pair-interleaved copy w1p[C][w1p_elems] ([k quad][output pair][k in quad][2]) that
+// k_pad / k_finalize keep in step with theta_pad.
+__host__ __device__ inline int w1p_quad_stride(int out_p) { return 4 * out_p + 4; }
+__host__ __device__ inline int w1p_elems(const ModelPlan& mp) { return (mp.b[0].in_p >> 2) * w1p_quad_stride(mp.b[0].out_p); }
 bool wide2_supported(const ModelPlan& mp);
 bool plan_wide2(const ModelPlan& mp, ModelPlan& wp, size_t smem_limit);
-void launch_sweep_wide2(const ModelPlan& wp, int C, int S, const float* theta_pad, const float* X,
-                        const float* Y, long long N, float* partial, double* stat_part, cudaStream_t st);
+void launch_sweep_wide2(const ModelPlan& wp, int C, int S, const float* theta_pad, const float* w1p,
+                        const float* X, const float* Y, long long N, float* partial, double* stat_part,
+                        cudaStream_t st);
 
 // tcgen05 (3xTF32) posterior-predictive sweep (k_predict_umma.cu), fp32 only; samples are FLAT [S][P].
 bool predict_umma_supported(const ModelPlan& mp);
