@@ -70,6 +70,12 @@ struct tbnn_handle {
   bool use_wide = false;
   bool use_wide2 = false;
   bool use_umma_predict = false;   // tcgen05 predictor (fp32, GEMM-shaped hidden layers)
+  bool want_usweep = false;        // tcgen05 wide-first-layer sweep allowed for this network / dtype / flags
+  bool use_usweep = false;         // ... and planned for the current data (after_data)
+  ModelPlan uw;                    // its tail plan
+  USweepPlan up;
+  void* Xt = nullptr;              // training matrix in core-matrix tiles (owned)
+  size_t Xt_cap = 0;
   ModelPlan pp;        // predictor (forward-only) plan
   int pp_rows = 0;     // rows per CTA of the predictor
   // data
@@ -313,6 +319,8 @@ extern "C" int tbnn_create(const tbnn_desc* d, tbnn_handle** out) {
   h->use_wide = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_WIDE) && plan_wide(h->mp, h->wp);
   h->use_wide2 = h->use_wide && !(d->flags & TBNN_FLAG_NO_WIDE2) && plan_wide2(h->mp, h->w2, SMEM_LIMIT);
   h->use_umma_predict = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_UMMA) && predict_umma_supported(h->mp);
+  h->want_usweep = d->dtype == TBNN_F32 && !(d->flags & (TBNN_FLAG_NO_WIDE | TBNN_FLAG_NO_UMMA | TBNN_FLAG_NO_UMMA_SWEEP)) &&
+                   usweep_supported(h->mp);
   if (plan_predict(h)) h->pp_rows = 0;   // predictor unavailable for this network/dtype; tbnn_predict reports it
   const ModelPlan& mp = h->mp;
   const size_t C = h->C, e = h->esz, pp = (size_t)mp.Ppad;
@@ -340,7 +348,7 @@ extern "C" int tbnn_destroy(tbnn_handle* h) {
   cudaSetDevice(h->device);
   void* ptrs[] = {h->theta_pad, h->theta0_pad, h->mom_pad, h->grad_pad, h->gsum, h->eps_dev, h->flat_tmp,
                   h->small_T, h->prior_part, h->dbl, h->ticket, h->partial, h->stat_part, h->X_own,
-                  h->Y_own, h->pred_ws, h->w1p};
+                  h->Y_own, h->pred_ws, h->w1p, h->Xt};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   delete h;
@@ -358,8 +366,8 @@ extern "C" int tbnn_predict_info(const tbnn_handle* h, int* kernel_kind) {
 extern "C" int tbnn_sweep_info(const tbnn_handle* h, int* kernel_kind, int* ctas_per_chain, int* rows_per_tile,
                                int* smem_bytes) {
   if (!h) return fail("null handle");
-  const ModelPlan& p = h->use_wide2 ? h->w2 : (h->use_wide ? h->wp : h->mp);
-  if (kernel_kind) *kernel_kind = h->use_wide2 ? 2 : (h->use_wide ? 1 : 0);
+  const ModelPlan& p = h->use_usweep ? h->uw : (h->use_wide2 ? h->w2 : (h->use_wide ? h->wp : h->mp));
+  if (kernel_kind) *kernel_kind = h->use_usweep ? 3 : (h->use_wide2 ? 2 : (h->use_wide ? 1 : 0));
   if (ctas_per_chain) *ctas_per_chain = h->S;
   if (rows_per_tile) *rows_per_tile = p.TR;
   if (smem_bytes) *smem_bytes = (int)((size_t)p.smem_elems * h->esz);
@@ -377,19 +385,20 @@ static int sync_n_total(tbnn_handle* h, cudaStream_t st) {
   return 0;
 }
 
-static int after_data(tbnn_handle* h, long long n_rows) {
+static int after_data(tbnn_handle* h, long long n_rows, cudaStream_t st = 0) {
   if (n_rows <= 0) return fail("n_rows must be positive");
   h->N = n_rows;
-  if (h->use_wide) {
-    // row-granular balanced split: every CTA gets N/S (+-1) rows, at least 8
-    long long smax = std::max(1, h->num_sms / h->C);
-    h->S = (int)std::max<long long>(1, std::min<long long>(smax, (n_rows + 7) / 8));
-  } else {
+  {
+    const long long smax = std::max(1, h->num_sms / h->C);
+    // row-granular balanced split (wide-first-layer sweeps): every CTA gets N/S (+-1) rows, at least 8
+    const int s_row = (int)std::max<long long>(1, std::min<long long>(smax, (n_rows + 7) / 8));
+    // tile-granular split (generic tile engine)
     const long long ntile = (n_rows + h->mp.TR - 1) / h->mp.TR;
-    long long smax = std::max(1, h->num_sms / h->C);
-    smax = std::min(smax, ntile);
-    const long long q = (ntile + smax - 1) / smax;
-    h->S = (int)((ntile + q - 1) / q);
+    const long long sm2 = std::min(smax, ntile);
+    const long long q = (ntile + sm2 - 1) / sm2;
+    const int s_tile = (int)((ntile + q - 1) / q);
+    h->use_usweep = h->want_usweep && plan_usweep(h->mp, n_rows, s_row, SMEM_LIMIT, h->uw, h->up);
+    h->S = (h->use_wide || h->use_usweep) ? s_row : s_tile;
   }
   const size_t need = (size_t)h->C * h->S * h->mp.Ppad * h->esz;
   if (need > h->partial_cap) {
@@ -398,6 +407,19 @@ static int after_data(tbnn_handle* h, long long n_rows) {
     CU(cudaMalloc(&h->partial, need));
     CU(cudaMalloc(&h->stat_part, (size_t)h->C * h->num_sms * sizeof(double) + 64));
     h->partial_cap = need;
+  }
+  // tcgen05 sweep: plan for this N / S and re-lay the training matrix into core-matrix tiles
+  if (h->use_usweep) {
+    const size_t xb = usweep_xt_bytes(h->up);
+    if (xb > h->Xt_cap) {
+      if (h->Xt) cudaFree(h->Xt);
+      h->Xt = nullptr; h->Xt_cap = 0;
+      CU(cudaMalloc(&h->Xt, xb));
+      h->Xt_cap = xb;
+    }
+    launch_tile_x(h->up, h->mp.D, (const float*)h->X, n_rows, (float*)h->Xt, st);
+    h->launches++;
+    CU(cudaGetLastError());
   }
   return sync_n_total(h, 0);
 }
@@ -419,13 +441,16 @@ extern "C" int tbnn_set_data_host(tbnn_handle* h, const void* X, const void* Y, 
   CU(cudaMemcpyAsync(h->X_own, X, xb, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(h->Y_own, Y, yb, cudaMemcpyHostToDevice, st));
   h->X = h->X_own; h->Y = h->Y_own;
-  return after_data(h, n_rows);
+  return after_data(h, n_rows, st);
 }
 
 // the row sweep: wide-first-layer kernel when planned (fp32), else the generic tile engine
 template <typename T>
 static void sweep(tbnn_handle* h, bool backward, cudaStream_t st) {
-  if (h->use_wide2 && backward) {
+  if (h->use_usweep && backward) {
+    launch_sweep_umma(h->uw, h->up, h->C, h->S, (const float*)h->theta_pad, (const float*)h->Xt, (const float*)h->Y,
+                      h->N, (float*)h->partial, h->stat_part, st);
+  } else if (h->use_wide2 && backward) {
     launch_sweep_wide2(h->w2, h->C, h->S, (const float*)h->theta_pad, (const float*)h->w1p, (const float*)h->X,
                        (const float*)h->Y, h->N, (float*)h->partial, h->stat_part, st);
   } else if (h->use_wide) {

@@ -72,6 +72,27 @@ void launch_sweep_wide2(const ModelPlan& wp, int C, int S, const float* theta_pa
                         const float* X, const float* Y, long long N, float* partial, double* stat_part,
                         cudaStream_t st);
 
+// tcgen05 (3xTF32) wide-first-layer row sweep (k_sweep_umma.cu), fp32, forward + backward.  The training matrix is
+// re-laid once per tbnn_set_data into core-matrix tiles (launch_tile_x); the plan depends on N and S.
+struct USweepPlan {
+  int FC, nch;         // features per chunk (multiple of 8, <= 128); chunks = ceil((D + 1) / FC)
+  int TRc, ntiles;     // row capacity of a tile; tiles in total (tile t = rows [N t / ntiles, N (t+1) / ntiles))
+  int NP, NM;          // block-0 outputs as staged in shared memory (multiple of 8) / as the MMA's N (multiple of 16)
+  int xbytes, wbytes;  // bytes of one X chunk / of one W1 chunk (hi or lo)
+  int stage_bytes;     // X hi, X lo, W hi, W lo
+  int off_stage;       // byte offsets into dynamic shared memory
+  int off_dz, dzbytes, dz_cg;   // dZ1 operand (hi; lo at + dzbytes), its column-group stride
+  int off_wt, off_g, off_red;
+  int smem_bytes;
+};
+bool usweep_supported(const ModelPlan& mp);
+bool plan_usweep(const ModelPlan& mp, long long N, int S, size_t smem_limit, ModelPlan& wp, USweepPlan& up);
+size_t usweep_xt_bytes(const USweepPlan& up);
+void launch_tile_x(const USweepPlan& up, int D, const float* X, long long N, float* Xt, cudaStream_t st);
+void launch_sweep_umma(const ModelPlan& wp, const USweepPlan& up, int C, int S, const float* theta_pad,
+                       const float* Xt, const float* Y, long long N, float* partial, double* stat_part,
+                       cudaStream_t st);
+
 // tcgen05 (3xTF32) posterior-predictive sweep (k_predict_umma.cu), fp32 only; samples are FLAT [S][P].
 bool predict_umma_supported(const ModelPlan& mp);
 bool launch_predict_umma(const ModelPlan& mp, int num_sms, const float* samples, long long s0, long long S_chunk,

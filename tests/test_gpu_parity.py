@@ -113,17 +113,21 @@ def test_logp_grad_matches_autograd_oracle(dtype):
                                           ("c2s", 9600, 1), ("c2s", 7, 2), ("wide_single", 333, 2),
                                           ("wide32", 97, 2), ("wide_sq", 5000, 1)])
 def test_wide_sweeps_equal_generic_engine(key, N, chains):
-    """The wide-first-layer kernels (warp-specialised k_sweep_wide2, phase-serial k_sweep_wide) and the generic
-    tile engine compute the same target (fp32): log-posterior, gradient, likelihood statistic."""
+    """The wide-first-layer kernels (tcgen05 3xTF32 k_sweep_umma, warp-specialised FFMA2 k_sweep_wide2, phase-serial
+    k_sweep_wide) and the generic tile engine compute the same target (fp32): log-posterior, gradient,
+    likelihood statistic."""
     from tensorbnn_b200 import _lib
     arch, lik, X, Y, TH, HY = problem(key, N, chains=chains)
     out = {}
-    for name, flags in (("default", 0), ("serial", _lib.FLAG_NO_WIDE2), ("generic", _lib.FLAG_NO_WIDE)):
+    for name, flags in (("default", 0), ("ffma2", _lib.FLAG_NO_UMMA_SWEEP),
+                        ("serial", _lib.FLAG_NO_UMMA_SWEEP | _lib.FLAG_NO_WIDE2), ("generic", _lib.FLAG_NO_WIDE)):
         eng = _engine(arch, lik, torch.float32, chains=chains, flags=flags)
         eng.set_data(X, Y)
         kern = eng.sweep_info()["kernel"]
         if name == "generic":
             assert kern == "k_partial"
+        elif name == "default":
+            assert kern == "k_sweep_umma"
         elif key == "wide32":
             assert kern == "k_partial"          # 896 x 32 weights + X tiles exceed shared memory: generic engine
         elif name == "serial":
@@ -132,19 +136,20 @@ def test_wide_sweeps_equal_generic_engine(key, N, chains):
             assert kern == "k_sweep_wide2"
         lp, g, st = eng.logp_grad(TH, HY)
         out[name] = (lp.cpu().numpy(), g.cpu().numpy(), st.cpu().numpy())
-    for name in ("default", "serial"):
+    for name in ("default", "ffma2", "serial"):
         assert np.allclose(out[name][0], out["generic"][0], rtol=2e-6, atol=0), name
         assert np.allclose(out[name][2], out["generic"][2], rtol=2e-6, atol=0), name
         assert rel(out[name][1], out["generic"][1]) <= 5e-6, name
 
 
-def test_wide_sweep_is_deterministic_and_matches_oracle():
+@pytest.mark.parametrize("flags,kernel", [(0, "k_sweep_umma"), (8, "k_sweep_wide2")])
+def test_wide_sweep_is_deterministic_and_matches_oracle(flags, kernel):
     """Run-to-run bit-identical results (fixed summation order) and 1e-5 agreement with the fp64 oracle at the
-    C2 shape (9,600 x 784, 784-20-20-1, Bernoulli)."""
+    C2 shape (9,600 x 784, 784-20-20-1, Bernoulli), for the tcgen05 sweep and the FFMA2 sweep."""
     arch, lik, X, Y, TH, HY = problem("c2s", 9600)
-    eng = _engine(arch, lik, torch.float32)
+    eng = _engine(arch, lik, torch.float32, flags=flags)
     eng.set_data(X, Y)
-    assert eng.sweep_info()["kernel"] == "k_sweep_wide2"
+    assert eng.sweep_info()["kernel"] == kernel
     lp1, g1, _ = eng.logp_grad(TH, HY)
     lp2, g2, _ = eng.logp_grad(TH, HY)
     assert torch.equal(lp1, lp2) and torch.equal(g1, g2)
@@ -152,6 +157,30 @@ def test_wide_sweep_is_deterministic_and_matches_oracle():
     lp_ref, g_ref = analytic.main_value_and_grad(arch, lik, r32(TH[0]), r32(HY[0]), r32(X), r32(Y))
     assert abs(lp1.item() - lp_ref) <= 1e-5 * abs(lp_ref)
     assert rel(g1.cpu().numpy()[0], g_ref) <= 1e-5
+
+
+@pytest.mark.parametrize("N", [262144 + 37])
+def test_umma_sweep_many_tiles_per_cta(N):
+    """Large N: 128-row tiles, several tiles per CTA, dW1 accumulated in tensor memory across tiles; checked
+    against the FFMA2 sweep and through linearity in the rows (two halves sum to the whole)."""
+    from tensorbnn_b200 import _lib
+    arch, lik, X, Y, TH, HY = problem("c2s", N)
+    res = {}
+    for name, flags in (("umma", 0), ("ffma2", _lib.FLAG_NO_UMMA_SWEEP)):
+        eng = _engine(arch, lik, torch.float32, flags=flags)
+        eng.set_data(X, Y)
+        assert eng.sweep_info()["kernel"] == ("k_sweep_umma" if name == "umma" else "k_sweep_wide2")
+        lp, g, st = eng.logp_grad(TH, HY)
+        res[name] = (lp.item(), g.cpu().numpy()[0], st.cpu().numpy())
+        if name == "umma":
+            h = N // 2
+            parts = []
+            for sl in (slice(0, h), slice(h, N)):
+                eng.set_data(X[sl], Y[sl])
+                parts.append(eng.logp_grad(TH, HY)[2].cpu().numpy())
+            assert np.allclose(parts[0] + parts[1], res["umma"][2], rtol=1e-6)
+    assert abs(res["umma"][0] - res["ffma2"][0]) <= 5e-6 * abs(res["ffma2"][0])
+    assert rel(res["umma"][1], res["ffma2"][1]) <= 1e-5
 
 
 def test_bernoulli_saturation_matches_fp32_oracle():

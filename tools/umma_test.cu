@@ -14,7 +14,7 @@ using namespace tbnn;
 // mode bits: 1 = A MN-major (A given as [K][M]), 2 = B MN-major (B given as [K][N]), 4 = 3xTF32, 8 = A from TMEM
 // A given row-major as Amat[RA][CA]: K-major: [M=128][K]; MN-major: [K][M=128].  Same for B with N.
 __global__ void __launch_bounds__(128, 1)
-k_umma_test(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K, int mode) {
+k_umma_test(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K, int mode, int lay) {
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bar;
@@ -24,7 +24,10 @@ k_umma_test(const float* __restrict__ A, const float* __restrict__ B, float* __r
   const int RA = a_mn ? K : M, CA = a_mn ? M : K;
   const int RB = b_mn ? K : N, CB = b_mn ? N : K;
   // core-matrix strides: row groups contiguous (128 B), column groups at 128*(R/8)
-  const uint32_t rgA = 128, cgA = 128u * (RA / 8), rgB = 128, cgB = 128u * (RB / 8);
+  // lay 0: row groups contiguous (128 B), column groups at 128*(R/8); lay 1: column groups contiguous (128 B),
+  // row groups at 128*(C/4) (the layout of k_sweep_umma's X chunks)
+  const uint32_t rgA = lay ? 128u * (CA / 4) : 128u, cgA = lay ? 128u : 128u * (RA / 8);
+  const uint32_t rgB = lay ? 128u * (CB / 4) : 128u, cgB = lay ? 128u : 128u * (RB / 8);
   const uint32_t szA = (uint32_t)RA * CA * 4, szB = (uint32_t)RB * CB * 4;
   unsigned char* sAh = smraw;
   unsigned char* sAl = sAh + szA;
@@ -126,7 +129,8 @@ int main() {
   const int shapes[][2] = {{64, 64}, {32, 128}, {64, 128}, {64, 8}, {16, 32}, {256, 64}};   // {N, K}
   for (auto& sh : shapes) {
     const int N = sh[0], K = sh[1];
-    for (int mode = 0; mode < 16; ++mode) {
+    for (int ml = 0; ml < 32; ++ml) {
+      const int mode = ml & 15, lay = ml >> 4;
       if ((mode & 8) && ((mode & 1) || K > 128)) continue;
       std::vector<float> A(M * K), B(N * K), D(M * N, -1.f);
       srand(7 + mode + N);
@@ -139,7 +143,7 @@ int main() {
       cudaMemset(dD, 0xFF, D.size() * 4);
       const size_t smem = 2 * (size_t)(M * K + N * K) * 4 + 256;
       cudaFuncSetAttribute(k_umma_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_umma_test<<<1, 128, smem>>>(dA, dB, dD, N, K, mode);
+      k_umma_test<<<1, 128, smem>>>(dA, dB, dD, N, K, mode, lay);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("N=%d K=%d mode=%d CUDA error %s\n", N, K, mode, cudaGetErrorString(e)); return 2; }
       cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
@@ -162,7 +166,7 @@ int main() {
       const bool x3 = mode & 4;
       const double err = x3 ? e_exact : fmin(e_trunc, e_round);
       const bool ok = err <= (x3 ? 2e-6 : 2e-5) * fmax(scale, 1.0);
-      printf("N=%3d K=%3d A:%s%s B:%s %s  err_exact %.3e  err_vs_trunc %.3e  err_vs_round %.3e  %s\n", N, K,
+      printf("lay%d N=%3d K=%3d A:%s%s B:%s %s  err_exact %.3e  err_vs_trunc %.3e  err_vs_round %.3e  %s\n", lay, N, K,
              (mode & 1) ? "MN" : "K ", (mode & 8) ? "(tmem)" : "      ", (mode & 2) ? "MN" : "K ", x3 ? "3xTF32" : "1xTF32",
              e_exact, e_trunc, e_round, ok ? "ok" : "FAIL");
       fails += !ok;
