@@ -77,12 +77,12 @@ void launch_sweep_wide2(const ModelPlan& wp, int C, int S, const float* theta_pa
 struct USweepPlan {
   int FC, nch;         // features per chunk (multiple of 8, <= 128); chunks = ceil((D + 1) / FC)
   int TRc, ntiles;     // row capacity of a tile; tiles in total (tile t = rows [N t / ntiles, N (t+1) / ntiles))
-  int NP, NM;          // block-0 outputs as staged in shared memory (multiple of 8) / as the MMA's N (multiple of 16)
-  int xbytes, wbytes;  // bytes of one X chunk / of one W1 chunk (hi or lo)
-  int stage_bytes;     // X hi, X lo, W hi, W lo
+  int NP, NM;          // block-0 outputs staged per half (multiple of 8) / rows of a stacked [hi; lo] operand (64)
+  int xbytes, wbytes;  // bytes of one X chunk (hi or lo) / of one stacked W1 chunk
+  int stage_bytes;     // X hi, X lo, [W hi; W lo]
   int off_stage;       // byte offsets into dynamic shared memory
-  int off_dz, dzbytes, dz_cg;   // dZ1 operand (hi; lo at + dzbytes), its column-group stride
-  int off_wt, off_g, off_red;
+  int off_dz, dzbytes, dz_cg;   // stacked dZ1 operand, its column-group stride
+  int off_wt, off_g, off_red, off_dwx;   // tail parameters / accumulators, reduction scratch + barriers, drain buffer
   int smem_bytes;
 };
 bool usweep_supported(const ModelPlan& mp);

@@ -121,10 +121,17 @@ __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) 
   return base + ((uint32_t)lane << 16) + (uint32_t)col;
 }
 
-// ---- error-compensated split for 3xTF32: x = hi + lo with hi exactly representable in TF32
+// ---- error-compensated split for 3xTF32: x = hi + lo (+ 2^-23 |x|), hi and lo exactly representable in TF32.
+// Round to nearest on both parts: the tensor core itself TRUNCATES fp32 operands to TF32 (tools/umma_test.cu), which
+// on a truncated split leaves a one-sided error of up to 2^-21 |x| in every product -- visible as a bias in long sums.
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
+  hi = rn_tf32(x);
+  lo = rn_tf32(x - hi);
 }
 
 // byte offset of element (r, c) of a row-major matrix stored as 8x4 core matrices
