@@ -319,7 +319,7 @@ extern "C" int tbnn_create(const tbnn_desc* d, tbnn_handle** out) {
   h->use_wide = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_WIDE) && plan_wide(h->mp, h->wp);
   h->use_wide2 = h->use_wide && !(d->flags & TBNN_FLAG_NO_WIDE2) && plan_wide2(h->mp, h->w2, SMEM_LIMIT);
   h->use_umma_predict = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_UMMA) && predict_umma_supported(h->mp);
-  h->want_usweep = d->dtype == TBNN_F32 && !(d->flags & (TBNN_FLAG_NO_WIDE | TBNN_FLAG_NO_UMMA | TBNN_FLAG_NO_UMMA_SWEEP)) &&
+  h->want_usweep = d->dtype == TBNN_F32 && (d->flags & TBNN_FLAG_UMMA_SWEEP) && !(d->flags & (TBNN_FLAG_NO_WIDE | TBNN_FLAG_NO_UMMA)) &&
                    usweep_supported(h->mp);
   if (plan_predict(h)) h->pp_rows = 0;   // predictor unavailable for this network/dtype; tbnn_predict reports it
   const ModelPlan& mp = h->mp;

@@ -82,6 +82,7 @@ struct USweepPlan {
   int stage_bytes;     // X hi, X lo, [W hi; W lo]
   int off_stage;       // byte offsets into dynamic shared memory
   int off_dz, dzbytes, dz_cg;   // stacked dZ1 operand, its column-group stride
+  int off_wtt, wtt_ofs[MAXB];   // transposed weights of blocks >= 1 (floats from off_wtt)
   int off_wt, off_g, off_red, off_dwx;   // tail parameters / accumulators, reduction scratch + barriers, drain buffer
   int smem_bytes;
 };

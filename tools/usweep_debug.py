@@ -11,7 +11,7 @@ import test_gpu_parity as tp
 for key, N, chains in (("c2s", 96, 1), ("c2s", 9600, 1), ("wide_sq", 77, 2), ("wide_single", 40, 1), ("wide_prelu", 41, 1), ("wide32", 97, 1)):
     arch, lik, X, Y, TH, HY = tp.problem(key, N, chains=chains)
     res = {}
-    for name, flags in (("umma", 0), ("generic", _lib.FLAG_NO_WIDE)):
+    for name, flags in (("umma", _lib.FLAG_UMMA_SWEEP), ("generic", _lib.FLAG_NO_WIDE)):
         eng = Engine(arch, lik, dtype=torch.float32, chains=chains, flags=flags)
         eng.set_data(X, Y)
         lp, g, st = eng.logp_grad(TH, HY)
