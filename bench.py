@@ -52,6 +52,8 @@ def make_workload(name, rank=0):
         cfg = wl.c1("a")
     elif name == "c3":
         cfg = wl.c3(chains=148 * 2)
+    elif name == "c4":
+        cfg = wl.c4()
     else:
         raise ValueError(name)
     C = cfg["chains"]
@@ -161,6 +163,100 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_predictor(args):
+    """C5: posterior-predictive sweep (predictor.predict), fused per-row mean / sd mode.  One step = S_step stored
+    samples x M test rows on this rank's share of the samples; samples are split across ranks with no
+    communication, the per-row (count, mean, M2) triples are merged once at the end."""
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    from tensorbnn_b200 import parallel
+    from tensorbnn_b200.engine import Engine
+    S_step, M = args.pred_samples, args.pred_rows
+    cfg = wl.c5(M=M, S=S_step * world)
+    lo, hi = parallel.shard_range(S_step * world, rank, world)
+    eng = Engine(cfg["arch"], ("gaussian", 0.1), dtype=torch.float32, device=local_rank)
+    samples_h = torch.tensor(cfg["samples"][lo:hi], dtype=torch.float32).contiguous().pin_memory()
+    X_h = torch.tensor(cfg["X"], dtype=torch.float32).contiguous().pin_memory()
+    samples, X = samples_h.cuda(), X_h.cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.predict(samples, X, want_out=False, want_moments=True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    launches0 = eng.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        evs[i][0].record()
+        _, mom = eng.predict(samples, X, want_out=False, want_moments=True)
+        evs[i][1].record()
+    barrier()
+    gpu_launches = eng.launches - launches0
+    clk = clocks.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=eng.dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * S_step * M * args.steps / (dev_ms * 1e-3)
+    # end to end: samples and test rows from pinned host memory, merged mean / sd back to the host
+    out_h = torch.empty(2, mom.shape[1], M, dtype=torch.float32).pin_memory()
+    e2e_steps = max(2, args.steps // 2)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        flush.zero_()
+        s_d, x_d = samples_h.cuda(non_blocking=True), X_h.cuda(non_blocking=True)
+        _, mom = eng.predict(s_d, x_d, want_out=False, want_moments=True)
+        n, mu, m2 = parallel.merge_moments(mom[0], mom[1], mom[2])
+        out_h[0].copy_(mu, non_blocking=True)
+        out_h[1].copy_((m2 / torch.clamp(n - 1, min=1)).sqrt(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * S_step * M * e2e_steps / float(t.item())
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        F = sum(l[1] * l[2] for l in cfg["arch"] if l[0].startswith("dense"))
+        tflops = value * 2 * F / 1e12 / world
+        line = {"metric": "predictor sample-rows/sec", "value": value, "unit": "sample-rows/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3", "data": "synthetic",
+                "config": {"workload": "C5 slice", "samples_per_gpu": S_step, "test_rows": M, "network": "1-64-64-64-1",
+                           "mode": "fused per-row (count, mean, M2)", "parallelism": "samples split, one merge at the end",
+                           "l2": "flushed between timed steps (256 MB write)"},
+                "e2e": {"value": e2e_value, "unit": "sample-rows/s", "h2d_bytes_per_step": int(samples_h.numel() * 4 + X_h.numel() * 4),
+                        "d2h_bytes_per_step": int(out_h.numel() * 4), "steps": e2e_steps,
+                        "what": "per step: samples + test rows H2D, tbnn_predict (moments), merge, mean / sd D2H"},
+                "gpu_launches": int(gpu_launches), "clocks": clk,
+                "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2 / 3,
+                             "unit": "TFLOP/s", "frac": tflops / (peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2 / 3),
+                             "traffic": None, "kernel": eng.predict_kernel(), "peak_source": peak_src,
+                             "note": "useful fp32-equivalent flops (2F per sample-row); peak = measured bf16 dense / 2 "
+                                     "(tf32) / 3 (3xTF32 issues three MMAs per product)"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,9 +267,13 @@ def main():
     ap.add_argument("--leapfrog", type=int, default=0, help="override L (0 = workload default)")
     ap.add_argument("--ref-leapfrog", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pred-samples", type=int, default=512, help="c5: stored samples per GPU and step")
+    ap.add_argument("--pred-rows", type=int, default=1048576, help="c5: test rows")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        return run_predictor(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -192,6 +292,14 @@ def main():
     eps = cfg["eps"]
     dt = torch.float32
     eng = Engine(arch, lik, dtype=dt, chains=C, device=local_rank)
+    rows_sharded = args.workload == "c4" and world > 1
+    if rows_sharded:
+        # one chain, training rows split across the ranks, one NCCL all-reduce of the partial gradient per
+        # gradient evaluation inside libtbnn.so; every rank replays the identical chain
+        from tensorbnn_b200 import parallel
+        lo, hi = parallel.shard_range(len(cfg["X"]), rank, world)
+        cfg["X"], cfg["Y"] = cfg["X"][lo:hi], np.asarray(cfg["Y"])[lo:hi]
+        parallel.attach_row_sharding(eng, device=eng.dev)
     Xh = torch.tensor(cfg["X"], dtype=dt).contiguous().pin_memory()
     Yh = torch.tensor(np.asarray(cfg["Y"]).reshape(len(cfg["X"]), -1), dtype=dt).contiguous().pin_memory()
     eng.set_data(Xh.cuda(), Yh.cuda())
@@ -207,7 +315,7 @@ def main():
 
     # ---------------- device-resident throughput ("value")
     for i in range(args.warmup):
-        eng.hmc_step(th, hy, 1 + rank, i, eps, L, stats=stats)
+        eng.hmc_step(th, hy, 1 + (0 if rows_sharded else rank), i, eps, L, stats=stats)
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -216,7 +324,7 @@ def main():
     for i in range(args.steps):
         flush.zero_()                                   # evict L2 between timed iterations
         evs[i][0].record()
-        eng.hmc_step(th, hy, 1 + rank, args.warmup + i, eps, L, stats=stats)
+        eng.hmc_step(th, hy, 1 + (0 if rows_sharded else rank), args.warmup + i, eps, L, stats=stats)
         evs[i][1].record()
     barrier()
     gpu_launches = eng.launches - launches0
@@ -226,7 +334,8 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
-    value = world * C * L * args.steps / (dev_ms * 1e-3)
+    units = 1 if rows_sharded else world          # row sharding: ONE chain advanced by all ranks together
+    value = units * C * L * args.steps / (dev_ms * 1e-3)
     accept = float(stats[:, 1].mean().item())
 
     # ---------------- end to end through the C ABI with HOST buffers
@@ -242,7 +351,7 @@ def main():
         eng.set_data_host(Xh, Yh)                       # training set from pinned host memory
         th.copy_(th_h, non_blocking=True)
         hy.copy_(hy_h, non_blocking=True)
-        eng.hmc_step(th, hy, 1 + rank, 10_000 + i, eps, L, stats=stats)
+        eng.hmc_step(th, hy, 1 + (0 if rows_sharded else rank), 10_000 + i, eps, L, stats=stats)
         th_o.copy_(th, non_blocking=True)
         st_o.copy_(stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -259,7 +368,7 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * C * L * e2e_steps / float(t.item())
+    e2e_value = units * C * L * e2e_steps / float(t.item())
     eng.set_data(Xh.cuda(), Yh.cuda())
 
     # ---------------- roofline of the dominant kernel (row sweep), CUDA events inside the library
@@ -292,11 +401,12 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if rows_sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"], "rows": int(cfg["X"].shape[0]), "features": int(cfg["X"].shape[1]),
                        "network": "-".join(str(d) for d in [arch[0][1]] + [l[2] for l in arch if l[0].startswith("dense")]),
                        "likelihood": lik[0], "chains_per_gpu": C, "leapfrog_per_step": L, "step_size": eps,
-                       "parallelism": "chains split, no communication" if world > 1 else "single chain",
+                       "parallelism": ("rows sharded, one NCCL all-reduce per gradient evaluation" if rows_sharded else
+                                       "chains split, no communication" if world > 1 else "single chain"),
                        "l2": "flushed between timed steps (256 MB write); within a trajectory the data is L2-resident"},
             "us_per_leapfrog": 1e3 * dev_ms / (args.steps * L),
             "accept_prob_last": accept,

@@ -76,6 +76,14 @@ struct tbnn_handle {
   USweepPlan up;
   void* Xt = nullptr;              // training matrix in core-matrix tiles (owned)
   size_t Xt_cap = 0;
+  // CUDA graphs of 2^k interior leapfrog steps (sweep + finalize each), replayed instead of 2 * 2^k launches;
+  // valid for one (hyper pointer, data epoch), rebuilt when either changes
+  static constexpr int GRAPH_LOG2_MAX = 5;
+  cudaGraphExec_t step_graph[GRAPH_LOG2_MAX + 1] = {};
+  const void* graph_hyper = nullptr;
+  uint64_t graph_epoch = 0, data_epoch = 1;
+  cudaStream_t cap_stream = nullptr;
+  bool graphs_off = false;
   ModelPlan pp;        // predictor (forward-only) plan
   int pp_rows = 0;     // rows per CTA of the predictor
   // data
@@ -350,6 +358,8 @@ extern "C" int tbnn_destroy(tbnn_handle* h) {
                   h->small_T, h->prior_part, h->dbl, h->ticket, h->partial, h->stat_part, h->X_own,
                   h->Y_own, h->pred_ws, h->w1p, h->Xt};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& g : h->step_graph) if (g) cudaGraphExecDestroy(g);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   delete h;
   return 0;
@@ -388,6 +398,7 @@ static int sync_n_total(tbnn_handle* h, cudaStream_t st) {
 static int after_data(tbnn_handle* h, long long n_rows, cudaStream_t st = 0) {
   if (n_rows <= 0) return fail("n_rows must be positive");
   h->N = n_rows;
+  h->data_epoch++;                 // cached leapfrog graphs point at the old data / partial buffers
   {
     const long long smax = std::max(1, h->num_sms / h->C);
     // row-granular balanced split (wide-first-layer sweeps): every CTA gets N/S (+-1) rows, at least 8
@@ -530,12 +541,51 @@ extern "C" int tbnn_logp_grad(tbnn_handle* h, const void* theta, const void* hyp
                               : logp_grad_impl<double>(h, theta, hyper, logp, grad, lik_stat, (cudaStream_t)stream);
 }
 
+// CUDA graph of n = 2^k interior leapfrog steps (coefficients {1, 0, 1}, no log-posterior output), captured on a
+// private stream and replayed on the caller's; nullptr when graphs are unavailable (NCCL row sharding, a failed
+// capture), in which case the caller launches the kernels directly.
+template <typename T>
+static cudaGraphExec_t interior_graph(tbnn_handle* h, const T* hyper, int k) {
+  if (h->graphs_off || h->comm) return nullptr;
+  if (h->graph_hyper != (const void*)hyper || h->graph_epoch != h->data_epoch) {
+    for (auto& g : h->step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    h->graph_hyper = hyper; h->graph_epoch = h->data_epoch;
+  }
+  if (h->step_graph[k]) return h->step_graph[k];
+  if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    h->graphs_off = true; cudaGetLastError(); return nullptr;
+  }
+  cudaGraph_t graph = nullptr;
+  const int64_t launches0 = h->launches;
+  bool ok = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+  if (ok) {
+    for (int j = 0; j < (1 << k) && ok; ++j)
+      ok = eval_step<T>(h, hyper, StepCoef{1.0, 0.0, 1.0}, nullptr, nullptr, h->cap_stream) == 0;
+    ok = (cudaStreamEndCapture(h->cap_stream, &graph) == cudaSuccess) && ok && graph;
+  }
+  h->launches = launches0;             // nothing ran yet: replays are counted where they are launched
+  if (ok) ok = cudaGraphInstantiate(&h->step_graph[k], graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) { h->graphs_off = true; h->step_graph[k] = nullptr; cudaGetLastError(); return nullptr; }
+  return h->step_graph[k];
+}
+
 // leapfrog on the padded state held in the handle (TFP order)
 template <typename T>
 static int leapfrog_impl(tbnn_handle* h, const T* hyper, int L, double* logp_first, double* stat_first,
                          double* logp_last, double* stat_last, cudaStream_t st) {
   CK(eval_step<T>(h, hyper, StepCoef{0.5, 0.0, 1.0}, logp_first, stat_first, st));
-  for (int j = 1; j < L; ++j) CK(eval_step<T>(h, hyper, StepCoef{1.0, 0.0, 1.0}, nullptr, nullptr, st));
+  int left = L - 1;                    // interior steps: graphs of 32, 16, ... steps, then single launches
+  for (int k = tbnn_handle::GRAPH_LOG2_MAX; k >= 1 && left > 0; --k) {
+    while (left >= (1 << k)) {
+      cudaGraphExec_t g = interior_graph<T>(h, hyper, k);
+      if (!g) break;
+      CU(cudaGraphLaunch(g, st));
+      h->launches += 2 << k;
+      left -= 1 << k;
+    }
+  }
+  for (; left > 0; --left) CK(eval_step<T>(h, hyper, StepCoef{1.0, 0.0, 1.0}, nullptr, nullptr, st));
   CK(eval_step<T>(h, hyper, StepCoef{1.0, 0.5, 0.0}, logp_last, stat_last, st));
   return 0;
 }
