@@ -517,6 +517,123 @@ void Launch<T>::mh(const ModelPlan& mp, int C, uint64_t seed, uint64_t call, con
                              stat0, stat1, stat_cur, theta_flat, stats);
 }
 
+// ------------------------------------------------------------------ persistent trajectory (small problems)
+// One CTA per chain runs the WHOLE L-step leapfrog trajectory (L + 1 log-posterior + gradient evaluations, TFP
+// order: SURVEY App. B) in one launch when the training set is a single tile: the X tile, the parameters and the
+// gradient accumulators stay in shared memory, the momentum in registers, and nothing goes through HBM or the host
+// between steps.  Replaces 2 (L + 1) launches of k_partial + k_finalize at the reference's own example size
+// (Examples/trainRegression.py: 11 rows, 251 parameters), where launch latency was the whole cost.
+// Same arithmetic as k_partial (S = 1) + k_finalize.
+constexpr int TRAJ_EPT = 8;    // parameters per thread (Ppad <= TRAJ_EPT * NT)
+template <typename T>
+__global__ void __launch_bounds__(NT, 1)
+k_traj_small(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, const T* __restrict__ Y, long long N,
+             const T* __restrict__ hyper, long long Ntot, T* __restrict__ theta_pad, T* __restrict__ mom_pad,
+             T* __restrict__ grad_pad, const T* __restrict__ eps_dev, int L, double* __restrict__ logp_first,
+             double* __restrict__ stat_first, double* __restrict__ logp_last, double* __restrict__ stat_last) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  T* sm = reinterpret_cast<T*>(smraw);
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const T* hy = hyper + (size_t)c * mp.H;
+  T* thg = theta_pad + (size_t)c * mp.Ppad;
+  TileCtx<T> cx;
+  cx.sm = sm;
+  cx.G = sm + mp.offG;
+  T* Ws = sm + mp.offW;
+  cx.Wp = Ws;
+  for (int i = tid; i < mp.Ppad; i += NT) Ws[i] = thg[i];
+  T p[TRAJ_EPT], gt[TRAJ_EPT];
+#pragma unroll
+  for (int k = 0; k < TRAJ_EPT; ++k) {
+    const int i = tid + k * NT;
+    p[k] = i < mp.Ppad ? mom_pad[(size_t)c * mp.Ppad + i] : T(0);
+    gt[k] = T(0);
+  }
+  load_x_tile<T>(mp, sm + mp.offX, X, 0, (int)N);
+  wait_x_tile();
+  double sg = 1.0, scale = 1.0;
+  if (mp.lik == LIK_GAUSS) {
+    const double h = (double)hy[mp.lik_h];
+    sg = fmin(fmax(h * h, 1e-8), 1e8);
+    scale = 1.0 / (sg * sg);
+  } else if (mp.lik == LIK_FIXED) {
+    sg = fmin(fmax(mp.fixed_sd, 1e-8), 1e8);
+    scale = 1.0 / (sg * sg);
+  }
+  const T eps = eps_dev[c];
+  double* red = reinterpret_cast<double*>(sm + mp.offRed);
+  for (int j = 0; j <= L; ++j) {
+    for (int i = tid; i < mp.Ppad; i += NT) cx.G[i] = T(0);
+    __syncthreads();
+    const T stat = tile_forward_backward<T>(mp, cx, Y, 0, (int)N);
+    const double st = block_sum((double)stat, red);       // barriers inside: G is complete afterwards
+    // gradient assembly + leapfrog update (k_finalize): step 0 {0.5, 0, 1}, interior {1, 0, 1}, last {1, 0.5, 0}
+    const T m1 = j == 0 ? T(0.5) : T(1), m2 = j == L ? T(0.5) : T(0);
+    const bool move = j < L;
+    double pv = 0.0;
+#pragma unroll
+    for (int k = 0; k < TRAJ_EPT; ++k) {
+      const int i = tid + k * NT;
+      if (i < mp.Ppad) {
+        const Elem e = decode_elem(mp, i);
+        if (e.kind) {
+          const T th = Ws[i];
+          double v = 0.0, pg = 0.0;
+          prior_elem<T>(mp, e, hy, (double)th, v, pg);
+          pv += v;
+          gt[k] = (T)((double)cx.G[i] * scale + pg);
+          p[k] = p[k] + (m1 * eps) * gt[k];
+          if (m2 != T(0)) p[k] = p[k] - (m2 * eps) * gt[k];
+          if (move) Ws[i] = th + eps * p[k];
+        } else {
+          gt[k] = T(0);
+        }
+      }
+    }
+    const bool want_first = j == 0 && logp_first != nullptr;
+    if (want_first || j == L) {
+      const double prior = block_sum(pv, red);
+      if (tid == 0) {
+        double ll;
+        if (mp.lik == LIK_BERN) {
+          ll = st;
+        } else {
+          const double n = (double)Ntot * (double)mp.OUT;
+          ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * 1.8378770664093453);
+        }
+        if (j == L) { logp_last[c] = prior + ll; if (stat_last) stat_last[c] = st; }
+        else { logp_first[c] = prior + ll; if (stat_first) stat_first[c] = st; }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < TRAJ_EPT; ++k) {
+    const int i = tid + k * NT;
+    if (i < mp.Ppad) {
+      const size_t gi = (size_t)c * mp.Ppad + i;
+      thg[i] = Ws[i];
+      mom_pad[gi] = p[k];
+      grad_pad[gi] = gt[k];
+    }
+  }
+}
+
+template <typename T>
+bool Launch<T>::traj_small_ok(const ModelPlan& mp, long long N, int S) {
+  return S == 1 && N <= mp.TR && mp.offW >= 0 && mp.offG >= 0 && mp.Ppad <= TRAJ_EPT * NT;
+}
+template <typename T>
+void Launch<T>::traj_small(const ModelPlan& mp, int C, const T* X, const T* Y, long long N, const T* hyper,
+                           long long N_total, T* theta_pad, T* mom_pad, T* grad_pad, const T* eps_dev, int L,
+                           double* logp_first, double* stat_first, double* logp_last, double* stat_last,
+                           cudaStream_t st) {
+  const size_t smem = (size_t)mp.smem_elems * sizeof(T);
+  cudaFuncSetAttribute(k_traj_small<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_traj_small<T><<<C, NT, smem, st>>>(mp, X, Y, N, hyper, N_total, theta_pad, mom_pad, grad_pad, eps_dev, L,
+                                       logp_first, stat_first, logp_last, stat_last);
+}
+
 template struct Launch<float>;
 template struct Launch<double>;
 

@@ -32,6 +32,13 @@ template <typename T> struct Launch {
                        const T* gsum, const T* hyper, long long N_total, T* theta_pad, T* mom_pad,
                        T* grad_pad, const T* eps_dev, StepCoef cf, double* logp, double* stat_out,
                        double* prior_part, unsigned* ticket, cudaStream_t st, T* w1p = nullptr);
+  // whole L-step trajectory in ONE launch (one CTA per chain) when the training set is a single tile and the
+  // parameters fit the shared-memory plan; same arithmetic as partial (S = 1) + finalize
+  static bool traj_small_ok(const ModelPlan& mp, long long N, int S);
+  static void traj_small(const ModelPlan& mp, int C, const T* X, const T* Y, long long N, const T* hyper,
+                         long long N_total, T* theta_pad, T* mom_pad, T* grad_pad, const T* eps_dev, int L,
+                         double* logp_first, double* stat_first, double* logp_last, double* stat_last,
+                         cudaStream_t st);
   // momentum ~ N(0, I) (Philox) or copy of injected flat momentum; ke[c] = 0.5*sum p^2
   static void momentum(const ModelPlan& mp, int C, uint64_t seed, uint64_t call, const T* injected_flat,
                        T* mom_pad, double* ke, cudaStream_t st);
