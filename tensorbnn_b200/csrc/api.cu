@@ -84,6 +84,8 @@ struct tbnn_handle {
   uint64_t graph_epoch = 0, data_epoch = 1;
   cudaStream_t cap_stream = nullptr;
   bool graphs_off = false;
+  ModelPlan np;                    // plan of the narrow-network persistent trajectory kernel
+  bool has_narrow = false;
   bool no_persistent = false;      // TBNN_FLAG_NO_PERSISTENT: never use the one-launch trajectory kernel
   ModelPlan pp;        // predictor (forward-only) plan
   int pp_rows = 0;     // rows per CTA of the predictor
@@ -328,6 +330,9 @@ extern "C" int tbnn_create(const tbnn_desc* d, tbnn_handle** out) {
   h->use_wide = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_WIDE) && plan_wide(h->mp, h->wp);
   h->use_wide2 = h->use_wide && !(d->flags & TBNN_FLAG_NO_WIDE2) && plan_wide2(h->mp, h->w2, SMEM_LIMIT);
   h->no_persistent = (d->flags & TBNN_FLAG_NO_PERSISTENT) != 0;
+  h->has_narrow = !(d->flags & TBNN_FLAG_NO_NARROW) &&
+                  (d->dtype == TBNN_F32 ? Launch<float>::plan_traj_narrow(h->mp, h->np, SMEM_LIMIT)
+                                        : Launch<double>::plan_traj_narrow(h->mp, h->np, SMEM_LIMIT));
   h->use_umma_predict = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_UMMA) && predict_umma_supported(h->mp);
   h->want_usweep = d->dtype == TBNN_F32 && (d->flags & TBNN_FLAG_UMMA_SWEEP) && !(d->flags & (TBNN_FLAG_NO_WIDE | TBNN_FLAG_NO_UMMA)) &&
                    usweep_supported(h->mp);
@@ -576,6 +581,15 @@ static cudaGraphExec_t interior_graph(tbnn_handle* h, const T* hyper, int k) {
 template <typename T>
 static int leapfrog_impl(tbnn_handle* h, const T* hyper, int L, double* logp_first, double* stat_first,
                          double* logp_last, double* stat_last, cudaStream_t st) {
+  if (!h->comm && !h->no_persistent && h->has_narrow && h->N <= 64) {
+    // narrow networks on a few rows: the whole trajectory in one launch, one row per half-warp (k_traj_narrow)
+    Launch<T>::traj_narrow(h->np, h->C, (const T*)h->X, (const T*)h->Y, h->N, hyper, h->N_total, (T*)h->theta_pad,
+                           (T*)h->mom_pad, (T*)h->grad_pad, (const T*)h->eps_dev, L, logp_first, stat_first,
+                           logp_last, stat_last, st);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+  }
   if (!h->comm && !h->no_persistent && !h->use_wide && Launch<T>::traj_small_ok(h->mp, h->N, h->S)) {
     // small problems: the whole trajectory in one persistent launch (k_traj_small)
     Launch<T>::traj_small(h->mp, h->C, (const T*)h->X, (const T*)h->Y, h->N, hyper, h->N_total, (T*)h->theta_pad,

@@ -3,6 +3,7 @@
 // Metropolis-Hastings select.  Reference call sites: network.py:370-392 (target),
 // :394-411 (HMC transition); TFP leapfrog / MH semantics per SURVEY.md Appendix B.
 #include "engine.cuh"
+#include "narrow.cuh"
 #include "kernels.h"
 #include "philox.cuh"
 
@@ -632,6 +633,189 @@ void Launch<T>::traj_small(const ModelPlan& mp, int C, const T* X, const T* Y, l
   cudaFuncSetAttribute(k_traj_small<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_traj_small<T><<<C, NT, smem, st>>>(mp, X, Y, N, hyper, N_total, theta_pad, mom_pad, grad_pad, eps_dev, L,
                                        logp_first, stat_first, logp_last, stat_last);
+}
+
+// ------------------------------------------------------------------ persistent trajectory (narrow networks)
+// Same job as k_traj_small for networks whose every width (input included) is <= 32 and whose training set is
+// <= 64 rows -- the reference's own example (Examples/trainRegression.py: 11 rows, 1-10-10-10-1): one training row
+// per HALF-WARP (narrow.cuh: lane owns two neurons, no CTA barrier inside a row), so a gradient evaluation is a
+// handful of barriers instead of the tile engine's ~20 phases.
+constexpr int NARROW_ROWS = 64;
+template <typename T>
+__global__ void __launch_bounds__(NT, 1)
+k_traj_narrow(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, const T* __restrict__ Y, int N,
+              const T* __restrict__ hyper, long long Ntot, T* __restrict__ theta_pad, T* __restrict__ mom_pad,
+              T* __restrict__ grad_pad, const T* __restrict__ eps_dev, int L, double* __restrict__ logp_first,
+              double* __restrict__ stat_first, double* __restrict__ logp_last, double* __restrict__ stat_last) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  T* sm = reinterpret_cast<T*>(smraw);
+  const int c = blockIdx.x, tid = threadIdx.x, hw = tid >> 4, jl = tid & 15;
+  const BlockPlan& b0 = mp.b[0];
+  const T* hy = hyper + (size_t)c * mp.H;
+  T* thg = theta_pad + (size_t)c * mp.Ppad;
+  T* Ws = sm + mp.offW;
+  T* G = sm + mp.offG;
+  T* Xs = sm + mp.offX;
+  const int ld0 = mp.ld0, D = mp.D;
+  for (int i = tid; i < mp.Ppad; i += NT) Ws[i] = thg[i];
+  for (int e = tid; e < N * ld0; e += NT) {
+    const int r = e / ld0, k = e - r * ld0;
+    Xs[e] = k < D ? X[(long long)r * D + k] : T(0);
+  }
+  T p[TRAJ_EPT], gt[TRAJ_EPT];
+#pragma unroll
+  for (int k = 0; k < TRAJ_EPT; ++k) {
+    const int i = tid + k * NT;
+    p[k] = i < mp.Ppad ? mom_pad[(size_t)c * mp.Ppad + i] : T(0);
+    gt[k] = T(0);
+  }
+  double sg = 1.0, scale = 1.0;
+  if (mp.lik == LIK_GAUSS) {
+    const double h = (double)hy[mp.lik_h];
+    sg = fmin(fmax(h * h, 1e-8), 1e8);
+    scale = 1.0 / (sg * sg);
+  } else if (mp.lik == LIK_FIXED) {
+    sg = fmin(fmax(mp.fixed_sd, 1e-8), 1e8);
+    scale = 1.0 / (sg * sg);
+  }
+  const T eps = eps_dev[c];
+  double* red = reinterpret_cast<double*>(sm + mp.offRed);
+  __syncthreads();
+  for (int j = 0; j <= L; ++j) {
+    for (int i = tid; i < mp.Ppad; i += NT) G[i] = T(0);
+    // ---- rows: block 0 forward (lane owns outputs jl, jl + 16), then the narrow chain of the half-warp
+    T stat = T(0);
+    for (int r0 = 0; r0 < N; r0 += NT / 16) {
+      const int r = r0 + hw;
+      const bool active = r < N;
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int o = jl + 16 * i;
+          if (o < b0.out_p) {
+            T z = T(0), a = T(0);
+            if (o < b0.out) {
+              z = Ws[b0.pb + o];
+              const T* w = Ws + b0.pw + o * b0.ld_in;
+              const T* x = Xs + r * ld0;
+              for (int k = 0; k < b0.in_p; ++k) z = fma(w[k], x[k], z);
+              T slope = T(0);
+              if (act_keeps_z(b0.act)) slope = eff_slope<T>(b0.act, Ws + (b0.ps >= 0 ? b0.ps : 0), o, T(b0.alpha));
+              a = act_fwd<T>(b0.act, z, slope);
+            }
+            sm[b0.offS + r * b0.ld_out + o] = a;
+            if (b0.offZ >= 0) sm[b0.offZ + r * b0.ld_out + o] = z;
+          }
+        }
+      }
+      __syncwarp();
+      stat += narrow_row<T>(mp, Ws, sm, active ? r : 0, jl, active, Y, r, sm + b0.offD + (active ? r : 0) * b0.ld_out);
+    }
+    __syncthreads();
+    // ---- parameter gradients: blocks >= 1 from the row buffers (narrow_accum), block 0 against the X tile
+    if (mp.nb > 1) narrow_accum<T>(mp, Ws, G, sm, N, tid, NT);
+    for (int e = tid; e < b0.out_p * b0.in_p; e += NT) {
+      const int o = e / b0.in_p, k = e - o * b0.in_p;
+      T acc = T(0);
+      for (int r = 0; r < N; ++r) acc = fma(sm[b0.offD + r * b0.ld_out + o], Xs[r * ld0 + k], acc);
+      G[b0.pw + o * b0.ld_in + k] = acc;
+    }
+    for (int o = tid; o < b0.out_p; o += NT) {
+      T sb = T(0), sc = T(0);
+      for (int r = 0; r < N; ++r) {
+        sb += sm[b0.offD + r * b0.ld_out + o];
+        if (act_has_slopes(b0.act)) sc += sm[b0.offZ + r * b0.ld_out + o];
+      }
+      G[b0.pb + o] = sb;
+      if (act_has_slopes(b0.act)) G[b0.ps + o] = (b0.act == ACT_SQPRELU ? T(2) * Ws[b0.ps + o] : T(1)) * sc;
+    }
+    const double st = block_sum((double)stat, red);       // barriers inside: G is complete afterwards
+    // ---- gradient assembly + leapfrog update (k_finalize): step 0 {0.5, 0, 1}, interior {1, 0, 1}, last {1, 0.5, 0}
+    const T m1 = j == 0 ? T(0.5) : T(1), m2 = j == L ? T(0.5) : T(0);
+    const bool move = j < L;
+    double pv = 0.0;
+#pragma unroll
+    for (int k = 0; k < TRAJ_EPT; ++k) {
+      const int i = tid + k * NT;
+      if (i < mp.Ppad) {
+        const Elem e = decode_elem(mp, i);
+        if (e.kind) {
+          const T th = Ws[i];
+          double v = 0.0, pg = 0.0;
+          prior_elem<T>(mp, e, hy, (double)th, v, pg);
+          pv += v;
+          gt[k] = (T)((double)G[i] * scale + pg);
+          p[k] = p[k] + (m1 * eps) * gt[k];
+          if (m2 != T(0)) p[k] = p[k] - (m2 * eps) * gt[k];
+          if (move) Ws[i] = th + eps * p[k];
+        } else {
+          gt[k] = T(0);
+        }
+      }
+    }
+    const bool want_first = j == 0 && logp_first != nullptr;
+    if (want_first || j == L) {
+      const double prior = block_sum(pv, red);
+      if (tid == 0) {
+        double ll;
+        if (mp.lik == LIK_BERN) {
+          ll = st;
+        } else {
+          const double n = (double)Ntot * (double)mp.OUT;
+          ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * 1.8378770664093453);
+        }
+        if (j == L) { logp_last[c] = prior + ll; if (stat_last) stat_last[c] = st; }
+        else { logp_first[c] = prior + ll; if (stat_first) stat_first[c] = st; }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < TRAJ_EPT; ++k) {
+    const int i = tid + k * NT;
+    if (i < mp.Ppad) {
+      const size_t gi = (size_t)c * mp.Ppad + i;
+      thg[i] = Ws[i];
+      mom_pad[gi] = p[k];
+      grad_pad[gi] = gt[k];
+    }
+  }
+}
+
+// Plan of k_traj_narrow (offsets in elements): W, G, X tile [64][ld0], row buffers S_l / Z_l / dz_l [64][ld_out].
+template <typename T>
+bool Launch<T>::plan_traj_narrow(const ModelPlan& mp, ModelPlan& np, size_t smem_limit) {
+  if (mp.nb > 4 || mp.OUT > 32 || mp.Ppad > TRAJ_EPT * NT) return false;
+  for (int l = 0; l < mp.nb; ++l)
+    if (mp.b[l].in_p > 32 || mp.b[l].out_p > 32) return false;
+  np = mp;
+  np.TR = NARROW_ROWS;
+  int cur = 0;
+  np.offW = cur; cur += np.Ppad;
+  np.offG = cur; cur += np.Ppad;
+  np.offX = cur; cur += NARROW_ROWS * np.ld0;
+  for (int l = 0; l < np.nb; ++l) {
+    BlockPlan& b = np.b[l];
+    b.ksplit = 1;
+    b.offS = cur; cur += NARROW_ROWS * b.ld_out;
+    if (act_keeps_z(b.act)) { b.offZ = cur; cur += NARROW_ROWS * b.ld_out; } else b.offZ = -1;
+    b.offD = cur; cur += NARROW_ROWS * b.ld_out;
+  }
+  const int per8 = (int)(8 / sizeof(T));
+  cur = (cur + per8 - 1) / per8 * per8;
+  np.offRed = cur; cur += 64 * per8;
+  np.smem_elems = cur;
+  return (size_t)cur * sizeof(T) <= smem_limit;
+}
+template <typename T>
+void Launch<T>::traj_narrow(const ModelPlan& np, int C, const T* X, const T* Y, long long N, const T* hyper,
+                            long long N_total, T* theta_pad, T* mom_pad, T* grad_pad, const T* eps_dev, int L,
+                            double* logp_first, double* stat_first, double* logp_last, double* stat_last,
+                            cudaStream_t st) {
+  const size_t smem = (size_t)np.smem_elems * sizeof(T);
+  cudaFuncSetAttribute(k_traj_narrow<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_traj_narrow<T><<<C, NT, smem, st>>>(np, X, Y, (int)N, hyper, N_total, theta_pad, mom_pad, grad_pad, eps_dev, L,
+                                        logp_first, stat_first, logp_last, stat_last);
 }
 
 template struct Launch<float>;

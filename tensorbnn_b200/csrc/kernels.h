@@ -39,6 +39,12 @@ template <typename T> struct Launch {
                          long long N_total, T* theta_pad, T* mom_pad, T* grad_pad, const T* eps_dev, int L,
                          double* logp_first, double* stat_first, double* logp_last, double* stat_last,
                          cudaStream_t st);
+  // the same for narrow networks (every width <= 32, <= 64 rows): one row per half-warp (narrow.cuh)
+  static bool plan_traj_narrow(const ModelPlan& mp, ModelPlan& np, size_t smem_limit);
+  static void traj_narrow(const ModelPlan& np, int C, const T* X, const T* Y, long long N, const T* hyper,
+                          long long N_total, T* theta_pad, T* mom_pad, T* grad_pad, const T* eps_dev, int L,
+                          double* logp_first, double* stat_first, double* logp_last, double* stat_last,
+                          cudaStream_t st);
   // momentum ~ N(0, I) (Philox) or copy of injected flat momentum; ke[c] = 0.5*sum p^2
   static void momentum(const ModelPlan& mp, int C, uint64_t seed, uint64_t call, const T* injected_flat,
                        T* mom_pad, double* ke, cudaStream_t st);

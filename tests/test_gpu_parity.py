@@ -309,25 +309,27 @@ def test_trajectory_per_chain_step_sizes():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("key,N,chains", [("c1a", 11, 1), ("c1b", 11, 3), ("sqp", 40, 2), ("prelu", 29, 2), ("bern", 37, 1)])
+@pytest.mark.parametrize("key,N,chains", [("c1a", 11, 1), ("c1b", 11, 3), ("sqp", 40, 2), ("prelu", 29, 2), ("bern", 37, 1),
+                                          ("mixed", 64, 2), ("wide_out", 33, 1)])
 def test_persistent_trajectory_equals_launch_per_step(key, N, chains, dtype):
-    """k_traj_small (whole trajectory in one launch, single-tile problems) and the launch-per-step path
-    (k_partial + k_finalize, CUDA-graph replayed) run the same arithmetic: identical endpoints."""
+    """k_traj_narrow (one row per half-warp) and k_traj_small (tile engine), both the whole trajectory in one launch,
+    and the launch-per-step path (k_partial + k_finalize, CUDA-graph replayed) compute the same trajectory."""
     from tensorbnn_b200 import _lib
     arch, lik, X, Y, TH, HY = problem(key, N, chains=chains)
     rng = np.random.default_rng(11)
     p0 = rng.normal(size=TH.shape)
     out = []
-    for flags in (0, _lib.FLAG_NO_PERSISTENT):
+    for flags in (0, _lib.FLAG_NO_NARROW, _lib.FLAG_NO_PERSISTENT):
         eng = _engine(arch, lik, dtype, chains=chains, flags=flags)
         eng.set_data(X, Y)
         launches0 = eng.launches
         th1, p1, lp1, g1 = eng.trajectory(TH, HY, p0, 1e-3, 70)
         out.append((th1.cpu().numpy(), p1.cpu().numpy(), lp1.cpu().numpy(), g1.cpu().numpy(), eng.launches - launches0))
-    assert out[0][4] < 12 and out[1][4] >= 2 * 71          # one launch vs two per gradient evaluation
-    tol = 1e-6 if dtype == torch.float32 else 1e-13
-    for a, b in zip(out[0][:4], out[1][:4]):
-        assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+    assert out[0][4] < 12 and out[1][4] < 12 and out[2][4] >= 2 * 71     # one launch vs two per gradient evaluation
+    tol = 2e-6 if dtype == torch.float32 else 1e-12
+    for variant in (0, 1):
+        for a, b in zip(out[variant][:4], out[2][:4]):
+            assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max()), variant
 
 
 # ---------------------------------------------------------------------------- HMC transition
