@@ -163,7 +163,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def run_predictor(args):
+def run_predictor(args, restore_stdout):
     """C5: posterior-predictive sweep (predictor.predict), fused per-row mean / sd mode.  One step = S_step stored
     samples x M test rows on this rank's share of the samples; samples are split across ranks with no
     communication, the per-row (count, mean, M2) triples are merged once at the end."""
@@ -252,9 +252,25 @@ def run_predictor(args):
                              "note": "useful fp32-equivalent flops (2F per sample-row); peak = measured bf16 dense / 2 "
                                      "(tf32) / 3 (3xTF32 issues three MMAs per product)"},
                 "cpu_baseline": None}
+        restore_stdout()
         print(json.dumps(line))
+        sys.stdout.flush()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _stdout_to_stderr():
+    """Libraries (NCCL with NCCL_DEBUG=VERSION) write to fd 1; the contract is ONE JSON line on stdout.  Everything
+    goes to stderr until the returned function is called."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+
+    def restore():
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return restore
 
 
 def main():
@@ -272,8 +288,9 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    restore_stdout = _stdout_to_stderr()
     if args.workload == "c5":
-        return run_predictor(args)
+        return run_predictor(args, restore_stdout)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -415,7 +432,9 @@ def main():
                     "what": "per step: tbnn_set_data_host(X,Y) + theta/hyper H2D + tbnn_hmc_step + theta/stats D2H"},
             "gpu_launches": int(gpu_launches),
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+    restore_stdout()
     print(json.dumps(line))
+    sys.stdout.flush()
     if dist is not None:
         dist.destroy_process_group()
 
