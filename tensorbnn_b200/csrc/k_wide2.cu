@@ -9,10 +9,12 @@
 // The phase-serial predecessor (k_wide.cu) is latency bound (profiles/r1b_summary.md).  Here the stages of
 // a pass (<= 14 rows) run CONCURRENTLY on different passes, coupled only by mbarriers:
 //   producer warp : TMA bulk copies (cp.async.bulk -> mbarrier) of X rows into a ring of three tiles;
-//   F warps (5)   : block-0 forward z1 = X W1^T, split-K across warps and across 4 lane groups, register
+//   F warps (3)   : block-0 forward z1 = X W1^T, split-K across warps and across 4 lane groups, register
 //                   tile 4 rows x 2*NO outputs; packed fma.rn.f32x2 (SASS FFMA2) on OUTPUT pairs
 //                   (w[o][k], w[o+1][k]) read from a pair-interleaved copy of W1 against a broadcast x;
-//   T warps (2)   : cross-warp reduction + bias + activation of block 0, the narrow tail (blocks >= 1,
+//   T warps (2x2) : two groups of two warps; group g takes the passes p = g (mod 2), so two passes are inside the
+//                   tail at any time (it is the latency-critical stage: one group alone held the sweep at 51.7 us,
+//                   two give 45.4 us at C2).  Per pass: cross-warp reduction + bias + activation of block 0, the narrow tail (blocks >= 1,
 //                   widths <= 32: lane = (row pair, output quad), 2 x 4 register tiles), likelihood, data
 //                   gradient back to dz1 -- the latency-critical chain between F and B of a pass;
 //   A warp        : weight / bias / slope gradients of everything except W1, from double-buffered batch
@@ -27,10 +29,12 @@
 
 namespace tbnn {
 
-constexpr int W2_NF = 5;                 // forward warps
+constexpr int W2_NF = 3;                 // forward warps
 constexpr int W2_NB = 7;                 // backward warps (224 k-quads)
-constexpr int W2_NT = 2;                 // tail warps (8 rows each)
-constexpr int W2_THREADS = 32 * (W2_NF + W2_NB + W2_NT + 2);   // + accumulate warp + producer warp = 512
+constexpr int W2_NT = 2;                 // tail warps per group (8 rows each)
+constexpr int W2_NTG = 2;                // tail groups: group g takes the passes p = g (mod W2_NTG) -- the tail is the
+                                         // latency-critical stage, two passes are in flight in it at any time
+constexpr int W2_THREADS = 32 * (W2_NF + W2_NB + W2_NT * W2_NTG + 2);   // + accumulate warp + producer warp = 512
 constexpr int W2_TROWS = 16;             // rows of the forward register tiling (4 row groups x 4)
 constexpr int W2_NBUF = 3;               // X tiles in the ring
 constexpr int W2_MAXNO = 5;              // block-0 outputs <= 20 (register budget of the F / B tiles)
@@ -51,7 +55,7 @@ __device__ __forceinline__ float2 unpack2(u64 v) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
   return r;
 }
-__device__ __forceinline__ void t_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W2_NT) : "memory"); }
+__device__ __forceinline__ void t_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W2_NT * W2_NTG) : "memory"); }
 // waiting with back-off: the waiter is not on the critical path, leave the issue slots to the others
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(64);
@@ -205,7 +209,7 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
   }
   __syncthreads();
 
-  if (warp == W2_NF + W2_NB + W2_NT + 1) {
+  if (warp == W2_NF + W2_NB + W2_NT * W2_NTG + 1) {
     // ================================================================= producer
     if (lane == 0) {
       const uint32_t b1 = (uint32_t)(nch * QS * 4), b2 = (uint32_t)((mp.Ppad - b0.pb) * 4);
@@ -342,16 +346,16 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
         st4(out + b0.pw + o * ld0 + 4 * bt, v);
       }
     }
-  } else if (warp < W2_NF + W2_NB + W2_NT) {
+  } else if (warp < W2_NF + W2_NB + W2_NT * W2_NTG) {
     // ================================================================= T: tail, likelihood, dz1
     // lane = (row pair rp, output quad oq): rows row0, row0+1 of the pass, outputs 4oq..4oq+3 of every block
-    const int tw = warp - (W2_NF + W2_NB);
+    const int twa = warp - (W2_NF + W2_NB), tg = twa / W2_NT, tw = twa % W2_NT;
     const int rp = lane & 3, oq = lane >> 2, row0 = tw * 8 + 2 * rp, o0 = 4 * oq;
     const int OUT = mp.OUT;
     float stat = 0.f;
     const BlockPlan& bl = mp.b[NB - 1];
     mbar_wait(wbar, 0u);
-    for (int p = 0; p < npass; ++p) {
+    for (int p = tg; p < npass; p += W2_NTG) {
       const int b = p % W2_NBUF, zb = p & 1;
       const int lo = ps.lo(p), R = ps.size(p);
       const bool act[2] = {row0 < R, row0 + 1 < R};
@@ -502,11 +506,11 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
       }
     }
     const double ws = warp_sum((double)stat);
-    if (lane == 0) red[tw] = ws;
+    if (lane == 0) red[twa] = ws;
     t_barrier();
-    if (tw == 0 && lane == 0) {
+    if (twa == 0 && lane == 0) {
       double tot = 0.0;
-      for (int w = 0; w < W2_NT; ++w) tot += red[w];
+      for (int w = 0; w < W2_NT * W2_NTG; ++w) tot += red[w];
       stat_part[(size_t)c * S + s] = tot;
     }
   } else {
