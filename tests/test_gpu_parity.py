@@ -217,6 +217,61 @@ def test_padding_stays_zero_and_inputs_untouched():
     assert torch.equal(th, th0)
 
 
+# ---------------------------------------------------------------------------- BASELINE.json sizes, size-independent properties
+def test_c3_shape_batched_chains_are_independent():
+    """C3 shape (4,096 rows, 1-64-64-64-1 SquarePrelu): 64 chains evaluated in one launch give exactly what each chain
+    gives alone -- chains share the data and nothing else."""
+    cfg = wl.c3(chains=64)
+    arch, lik = cfg["arch"], cfg["lik"]
+    TH = np.stack([wl.init_theta(arch, seed=1000 + c, slope=cfg["slope"]) for c in range(64)])
+    HY = np.tile(wl.init_hyper(arch, lik), (64, 1))
+    eng = _engine(arch, lik, torch.float32, chains=64)
+    eng.set_data(cfg["X"], cfg["Y"])
+    lp, g, st = eng.logp_grad(TH, HY)
+    one = _engine(arch, lik, torch.float32, chains=1)
+    one.set_data(cfg["X"], cfg["Y"])
+    for c in (0, 17, 63):
+        lp1, g1, st1 = one.logp_grad(TH[c:c + 1], HY[c:c + 1])
+        assert abs(lp[c].item() - lp1.item()) <= 2e-6 * abs(lp1.item())
+        assert rel(g[c].cpu().numpy(), g1.cpu().numpy()[0]) <= 2e-6
+    # and the fp64 oracle on one of them (fp32 kernel, 1e-5)
+    r32 = lambda a: np.asarray(a).astype(np.float32).astype(np.float64)
+    lp_ref, g_ref = analytic.main_value_and_grad(arch, lik, r32(TH[17]), r32(HY[17]), r32(cfg["X"]), r32(cfg["Y"]))
+    assert abs(lp[17].item() - lp_ref) <= 1e-5 * abs(lp_ref)
+    assert rel(g[17].cpu().numpy(), g_ref) <= 1e-5
+
+
+def test_c4_full_size_linearity_in_rows():
+    """C4 at BASELINE size (4,194,304 x 32, 32-128-128-128-1): the likelihood statistic and the likelihood part of
+    the gradient are sums over rows.  With W = A u B and A = A1 u A2, every split leaves the same residual (the prior
+    gradient): g(A) + g(B) - g(W) = g(A1) + g(A2) - g(A); the statistic is exactly additive; reruns are bit-identical."""
+    N, D = 4194304, 32
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((N, D), dtype=np.float32)
+    Y = (X[:, :4].sum(axis=1) * 0.25 + 0.1 * rng.standard_normal(N, dtype=np.float32)).astype(np.float32)
+    arch = wl.mlp_arch([D, 128, 128, 128, 1], "dense", "relu")
+    lik = ("gaussian", 0.1)
+    th = wl.init_theta(arch, seed=0)[None]
+    hy = wl.init_hyper(arch, lik)[None]
+    eng = _engine(arch, lik, torch.float32)
+    Xd, Yd = eng.tensor(X), eng.tensor(Y)
+    res = {}
+    for name, sl in (("W", slice(0, N)), ("A", slice(0, N // 2)), ("B", slice(N // 2, N)),
+                     ("A1", slice(0, N // 4)), ("A2", slice(N // 4, N // 2))):
+        eng.set_data(Xd[sl], Yd[sl])
+        lp, g, st = eng.logp_grad(th, hy)
+        res[name] = (g.cpu().numpy()[0].astype(np.float64), float(st.item()))
+        if name == "W":
+            lp2, g2, st2 = eng.logp_grad(th, hy)
+            assert torch.equal(g, g2) and torch.equal(lp, lp2)
+    assert abs(res["A"][1] + res["B"][1] - res["W"][1]) <= 2e-6 * abs(res["W"][1])
+    assert abs(res["A1"][1] + res["A2"][1] - res["A"][1]) <= 2e-6 * abs(res["A"][1])
+    prior1 = res["A"][0] + res["B"][0] - res["W"][0]
+    prior2 = res["A1"][0] + res["A2"][0] - res["A"][0]
+    scale = np.abs(res["W"][0]).max()
+    assert np.abs(prior1 - prior2).max() <= 1e-5 * scale
+
+
 # ---------------------------------------------------------------------------- hyper target
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("key,N", [("c1a", 11), ("c1b", 11), ("sqp", 61), ("prelu", 29), ("c3s", 200),
