@@ -42,6 +42,25 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def ncu_traffic(kernel, workload):
+    """dram read + write bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the
+    same workload (profiles/), or None.  Cold-cache figure: in steady state C2's 30 MB set is L2-resident."""
+    if workload != "c2" or kernel != "k_sweep_wide2":
+        return None
+    try:
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1e_wide2_full_metrics.csv"))))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(k)
+            tot += float(vals[i].replace(",", "")) * scale.get(units[i], 1.0)
+        return tot
+    except Exception:
+        return None
+
+
 def make_workload(name, rank=0):
     if name == "c2":
         cfg = wl.c2()
@@ -394,7 +413,8 @@ def main():
     abytes = algorithmic_bytes_per_step(cfg, eng.P, 4, C)
     achieved = abytes / (avg_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": eng.sweep_info()["kernel"], "sweep": eng.sweep_info(),
+            "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(eng.sweep_info()["kernel"], args.workload),
+            "kernel": eng.sweep_info()["kernel"], "sweep": eng.sweep_info(),
             "launch_ms": avg_ms, "launch_ms_min": min_ms, "algorithmic_bytes_per_launch": abytes,
             "peak_source": peak_src,
             "fp32_tflops": C * flops_per_chain_step(cfg) / (avg_ms * 1e-3) / 1e12,
