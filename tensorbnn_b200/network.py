@@ -195,8 +195,13 @@ class network(object):
 
     # ------------------------------------------------------------------ sample store
     def _open_files(self, path, idx):
-        files = [open(os.path.join(path, "%d.%d.txt" % (n, idx)), "wb") for n in range(len(self.states))]
-        files.append(open(os.path.join(path, "hypers%d.txt" % idx), "wb"))
+        """Text files in the reference's layout (network.py:545-559) followed by their binary side-cars
+        (`<name>.f32`: the same values as raw little-endian float32 in the same order).  The reference's
+        predictor ignores the side-cars; this package's predictor reads them instead of parsing ~25 bytes of text
+        per value."""
+        names = ["%d.%d" % (n, idx) for n in range(len(self.states))] + ["hypers%d" % idx]
+        files = [open(os.path.join(path, nm + ".txt"), "wb") for nm in names]
+        files += [open(os.path.join(path, nm + ".f32"), "wb") for nm in names]
         return files
 
     def _chain_dirs(self, folderName):
@@ -299,6 +304,7 @@ class network(object):
                         fh.write(str(int(self._hyper.shape[1])).encode("utf-8"))
             # record a sample (reference network.py:647-663; one hyper scalar per line, Q5)
             if dirs and iter_ > startSampling and iter_ % samplingStep == 0:
+                nfile = len(self.states) + 1      # text handles first, then as many side-car handles
                 th = self._theta.detach().cpu().double().numpy()
                 hy = self._hyper.detach().cpu().double().numpy()
                 for c in range(C):
@@ -307,8 +313,10 @@ class network(object):
                         sh = tuple(s.shape[1:] if C > 1 else s.shape)
                         cnt = int(np.prod(sh))
                         np.savetxt(files[c][n], th[c, off:off + cnt].reshape(sh))
+                        th[c, off:off + cnt].astype("<f4").tofile(files[c][nfile + n])
                         off += cnt
-                    np.savetxt(files[c][-1], hy[c].reshape(-1, 1))
+                    np.savetxt(files[c][nfile - 1], hy[c].reshape(-1, 1))
+                    hy[c].astype("<f4").tofile(files[c][2 * nfile - 1])
             if verbose and iter_ % displaySkip == 0:
                 likelihood.display(self.hyperStates)
                 print("Time elapsed:", time.time() - startTime)

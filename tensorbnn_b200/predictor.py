@@ -8,6 +8,8 @@ materialising the [S, out, M] tensor.  reweight / autocorrelation are outside th
 accelerated hot path."""
 import math
 
+import os
+
 import numpy as np
 import torch
 
@@ -36,6 +38,14 @@ class predictor(object):
         self.weightsTrain = []
         self._engine = None
 
+    def _load_values(self, name, count, ndmin):
+        """`count` float32 values of file `name` (.txt in the reference's layout): from the binary side-car
+        `name.f32` when this package's writer left a complete one, else parsed from the text."""
+        side = self.directoryPath + name + ".f32"
+        if os.path.exists(side) and os.path.getsize(side) >= 4 * count:
+            return np.fromfile(side, dtype="<f4", count=count), True
+        return np.loadtxt(self.directoryPath + name + ".txt", dtype=np.float32, ndmin=ndmin), False
+
     def loadNetworks(self):
         """Parses summary.txt and the per-tensor text files (reference :43-113; values are read as
         float32 regardless of dtype, Q10)."""
@@ -56,15 +66,15 @@ class predictor(object):
             shapes.append((d1, d2) if len(summary[n]) == 2 else (d1,))
             w0 = np.zeros((total, d1, d2), dtype=np.float32)
             for m in range(numFiles):
-                w = np.loadtxt(self.directoryPath + "%d.%d.txt" % (n, m), dtype=np.float32, ndmin=2)
+                w, binary = self._load_values("%d.%d" % (n, m), numNetworks * d1 * d2, 2)
                 w0[m * numNetworks:(m + 1) * numNetworks] = \
-                    w[:numNetworks * d1, :d2].reshape(numNetworks, d1, d2)
+                    w.reshape(numNetworks, d1, d2) if binary else w[:numNetworks * d1, :d2].reshape(numNetworks, d1, d2)
             matrices.append(torch.as_tensor(w0).to(self.tdtype))
             flat_parts.append(w0.reshape(total, -1))
         hypers = []
         if numHypers > 0:
             for m in range(numFiles):
-                w = np.loadtxt(self.directoryPath + "hypers%d.txt" % m, dtype=np.float32, ndmin=1)
+                w, _ = self._load_values("hypers%d" % m, numNetworks * numHypers, 1)
                 for k in range(numNetworks):
                     hypers.append(w[numHypers * k:numHypers * (k + 1)])
         self.numNetworks = total

@@ -164,6 +164,32 @@ def test_file_roundtrip_and_lagging_summary(tmp_path):
     assert means[0].shape == (3, 2)
 
 
+def test_binary_side_cars_load_identically(tmp_path):
+    """`<name>.f32` side-cars (raw float32, same order) give the predictor exactly what parsing the
+    reference's text files gives; an incomplete side-car is ignored."""
+    from tensorbnn_b200.predictor import predictor
+    shapes = [(4, 3), (4, 1), (4,)]
+    rng = np.random.default_rng(1)
+    folder = str(tmp_path / "run3")
+    fileformat.write_run(folder, ["dense", "prelu"], 1000 + 60, 1000, 2, 10,
+                         lambda it: [rng.normal(size=s) for s in shapes], lambda it: rng.normal(size=5))
+    text = predictor(folder + "/", np.float32)
+    for name in os.listdir(folder):
+        if name.endswith(".txt") and name not in ("summary.txt", "architecture.txt"):
+            np.loadtxt(os.path.join(folder, name), dtype=np.float32).astype("<f4").tofile(
+                os.path.join(folder, name[:-4] + ".f32"))
+    binary = predictor(folder + "/", np.float32)
+    assert binary.numNetworks == text.numNetworks == 20      # lagging summary (Q9): the last file is not listed yet
+    for a, b in zip(binary.matrices, text.matrices):
+        assert torch.equal(a, b)
+    assert np.array_equal(np.array(binary.hypers), np.array(text.hypers))
+    # a truncated side-car must not be trusted
+    with open(os.path.join(folder, "0.0.f32"), "wb") as fh:
+        fh.write(b"\0" * 8)
+    again = predictor(folder + "/", np.float32)
+    assert torch.equal(again.matrices[0], text.matrices[0])
+
+
 def test_partial_last_file_is_invisible(tmp_path):
     """Q9: epochs that do not end on a rollover leave the last partial file out of the summary."""
     shapes = [(2, 2), (2, 1)]
