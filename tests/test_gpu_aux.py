@@ -1,6 +1,7 @@
 """GPU parity of the remaining hot-path rows: Philox momentum stream, adapter grid search
 (paramAdapter.gridSearch), posterior-predictive sweep (predictor.predict)."""
 import math
+import os
 import random
 
 import numpy as np
@@ -226,3 +227,41 @@ def test_predict_tensor_core_moments_accumulate_across_calls():
     mom = mom.cpu().numpy()
     assert np.abs(mom[1] - out.mean(axis=0)).max() <= 1e-5 * max(1.0, np.abs(out).max())
     assert np.abs(mom[2] / S - out.var(axis=0)).max() <= 1e-4 * out.var(axis=0).max() + 1e-9
+
+
+# ---------------------------------------------------------------------------- the drop-in Python surface end to end
+def test_train_writes_reference_layout_and_predictor_reads_it(tmp_path, monkeypatch):
+    """Examples/trainRegression.py in miniature through the reference's class API: network(...).add(...),
+    setupMCMC, train -> text files in the reference's layout (+ float32 side-cars) -> predictor.predict.
+    The side-cars hold exactly what parsing the text gives; predictions are finite and have the documented shape."""
+    from tensorbnn_b200.activationFunctions import Tanh
+    from tensorbnn_b200.layer import GaussianDenseLayer
+    from tensorbnn_b200.likelihood import FixedGaussianLikelihood
+    from tensorbnn_b200.metrics import SquaredError
+    from tensorbnn_b200.network import network
+    from tensorbnn_b200.predictor import predictor
+    monkeypatch.chdir(tmp_path)
+    x = np.linspace(-2, 2, 11)
+    y = np.sin(x * math.pi * 2) * x - np.cos(x * math.pi)
+    xv = np.linspace(-2 + 2 / 30, 2 - 2 / 30, 30)
+    yv = np.sin(xv * math.pi * 2) * xv - np.cos(xv * math.pi)
+    net = network(np.float32, 1, x, y, xv, yv)
+    for i, (a, b) in enumerate(((1, 10), (10, 10), (10, 1))):
+        net.add(GaussianDenseLayer(a, b, seed=10 + i))
+        if b != 1:
+            net.add(Tanh())
+    net.setupMCMC(0.001, 0.0001, 0.01, 20, 50, 10, 100, 10, 0.001, 10, 20, 2, 4)      # burnin = 20
+    net.train(20 + 41, 2, FixedGaussianLikelihood(sd=0.1), metricList=[SquaredError(mean=0, sd=1, scaleExp=False)],
+              folderName="run", networksPerFile=10, displaySkip=1000, verbose=False)
+    folder = str(tmp_path / "run") + "/"
+    names = sorted(os.listdir(folder))
+    assert "summary.txt" in names and "architecture.txt" in names and "0.0.txt" in names and "0.0.f32" in names
+    pr = predictor(folder, np.float32)
+    assert pr.numNetworks in (10, 20) and pr.numMatrices == 6     # lagging summary (Q9)
+    # side-car == parsed text
+    w_txt = np.loadtxt(folder + "0.0.txt", dtype=np.float32, ndmin=2)
+    w_bin = np.fromfile(folder + "0.0.f32", dtype="<f4")
+    assert np.array_equal(w_bin[:w_txt.size], w_txt.reshape(-1))
+    out = pr.predict(xv[:, None], n=5)
+    assert len(out) == pr.numNetworks // 5 and out[0].shape == (1, 30)
+    assert all(np.isfinite(o).all() for o in out)
