@@ -166,6 +166,27 @@ __device__ __forceinline__ void fwd_store(const BlockPlan& b, const T* Wp, T* S,
   if (Z) Z[r * b.ld_out + o] = z;
 }
 
+// the same with the bias and the effective slope of output o already in registers (one load per output column of a
+// thread tile instead of one per accumulator)
+template <typename T>
+__device__ __forceinline__ void fwd_store_pre(const BlockPlan& b, T* S, T* Z, int r, int o, T acc, T bias, T slope) {
+  T a = T(0), z = T(0);
+  if (o < b.out) {
+    z = acc + bias;
+    a = act_fwd<T>(b.act, z, slope);
+  }
+  S[r * b.ld_out + o] = a;
+  if (Z) Z[r * b.ld_out + o] = z;
+}
+template <typename T>
+__device__ __forceinline__ void load_bias_slope(const BlockPlan& b, const T* Wp, int o, T& bias, T& slope) {
+  bias = T(0); slope = T(0);
+  if (o < b.out) {
+    bias = Wp[b.pb + o];
+    if (act_keeps_z(b.act)) slope = eff_slope<T>(b.act, Wp + (b.ps >= 0 ? b.ps : 0), o, T(b.alpha));
+  }
+}
+
 // S_l[r][o] = act( sum_k A[r][k] W[o][k] + b[o] )       (layer.py:276-279 + activation)
 template <typename T>
 __device__ void fwd_block(const ModelPlan& mp, int l, const TileCtx<T>& cx) {
@@ -200,10 +221,13 @@ __device__ void fwd_block(const ModelPlan& mp, int l, const TileCtx<T>& cx) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[i][j] = fma(av[i][q], wv[j][q], acc[i][j]);
       }
+      T bias[4], slope[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) load_bias_slope<T>(b, cx.Wp, og + j * tn, bias[j], slope[j]);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) fwd_store<T>(b, cx.Wp, S, Z, rg + i * tm, og + j * tn, acc[i][j]);
+        for (int j = 0; j < 4; ++j) fwd_store_pre<T>(b, S, Z, rg + i * tm, og + j * tn, acc[i][j], bias[j], slope[j]);
     }
     __syncthreads();
   } else {
@@ -384,6 +408,11 @@ __device__ void bwd_block(const ModelPlan& mp, int l, const TileCtx<T>& cx, cons
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[i][q] = fma(dv[i][j], wv[j][q], acc[i][q]);
       }
+      T sl4[4] = {T(0), T(0), T(0), T(0)};
+      if (keepz) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sl4[q] = eff_slope<T>(pb.act, cx.Wp + (pb.ps >= 0 ? pb.ps : 0), 4 * kg + q, T(pb.alpha));
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = rg + i * tm;
@@ -394,7 +423,7 @@ __device__ void bwd_block(const ModelPlan& mp, int l, const TileCtx<T>& cx, cons
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const bool neg = zv[q] < T(0);
-            const T s = eff_slope<T>(pb.act, cx.Wp + (pb.ps >= 0 ? pb.ps : 0), 4 * kg + q, T(pb.alpha));
+            const T s = sl4[q];
             dzv[q] = neg ? acc[i][q] * s : acc[i][q];
             cv[q] = neg ? zv[q] * acc[i][q] : T(0);
           }
