@@ -208,7 +208,7 @@ __device__ void fwd_block(const ModelPlan& mp, int l, const TileCtx<T>& cx) {
         for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
       const T* a0 = A + rg * lda;
       const T* w0 = W + og * lda;
-#pragma unroll 2
+#pragma unroll 4
       for (int kc = 0; kc < kch; ++kc) {
         T av[4][4], wv[4][4];
 #pragma unroll
@@ -341,7 +341,7 @@ __device__ void bwd_block(const ModelPlan& mp, int l, const TileCtx<T>& cx, cons
         for (int q = 0; q < 4; ++q) acc[j][q] = T(0);
       const T* dz0 = dZ + 4 * og;
       const T* a0 = A + 4 * kg;
-#pragma unroll 4
+#pragma unroll 8
       for (int r = 0; r < TR; ++r) {
         T dv[4], av[4];
         ld4(dz0 + r * ldz, dv);
@@ -396,7 +396,7 @@ __device__ void bwd_block(const ModelPlan& mp, int l, const TileCtx<T>& cx, cons
         for (int q = 0; q < 4; ++q) acc[i][q] = T(0);
       const T* dz0 = dZ + rg * ldz;
       const T* w0 = W + 4 * kg;
-#pragma unroll 2
+#pragma unroll 4
       for (int oc = 0; oc < och; ++oc) {
         T dv[4][4], wv[4][4];
 #pragma unroll
