@@ -173,7 +173,10 @@ __device__ __forceinline__ void fwd_store_pre(const BlockPlan& b, T* S, T* Z, in
   T a = T(0), z = T(0);
   if (o < b.out) {
     z = acc + bias;
-    a = act_fwd<T>(b.act, z, slope);
+    // the two common kinds inline (uniform branches), the rest through the generic switch
+    if (act_keeps_z(b.act)) a = z < T(0) ? slope * z : z;
+    else if (b.act == ACT_RELU) a = z > T(0) ? z : T(0);
+    else a = act_fwd<T>(b.act, z, slope);
   }
   S[r * b.ld_out + o] = a;
   if (Z) Z[r * b.ld_out + o] = z;
