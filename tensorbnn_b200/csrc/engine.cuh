@@ -437,7 +437,8 @@ __device__ void bwd_block(const ModelPlan& mp, int l, const TileCtx<T>& cx, cons
           T av[4];
           ld4(Sp + r * lda + 4 * kg, av);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dzv[q] = acc[i][q] * act_deriv_from_out<T>(pb.act, av[q]);
+          for (int q = 0; q < 4; ++q)
+            dzv[q] = pb.act == ACT_RELU ? (av[q] > T(0) ? acc[i][q] : T(0)) : acc[i][q] * act_deriv_from_out<T>(pb.act, av[q]);
         }
         st4(dNext + r * lda + 4 * kg, dzv);
       }
