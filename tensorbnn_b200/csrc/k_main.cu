@@ -151,21 +151,26 @@ __global__ void k_reduce_partials(const __grid_constant__ ModelPlan mp, int S,
 // activationFunctions.py:189-190, :341-346 with the passed hyper slice, Q4).
 template <typename T>
 __device__ __forceinline__ void prior_elem(const ModelPlan& mp, const Elem& e, const T* hy, double x,
-                                           double& val, double& grad) {
+                                           double& val, double& grad, bool need_val = true) {
+  // need_val = false: gradient only (interior leapfrog steps never read the log-density; its fp64 log / log1p
+  // are most of the cost of this function)
   const BlockPlan& b = mp.b[e.blk];
   const double kLog2Pi = 1.8378770664093453;
+  val = 0.0;
   if (e.kind == 3) {
     if (b.act == ACT_SQPRELU) {
       const double mean = (double)hy[b.ha];
       double sd = (double)hy[b.ha + 1];
       sd = fmin(fmax(sd, 1e-8), 1e8);
       const double d = (x - mean) / sd;
-      val = -0.5 * d * d;
       grad = -d / sd;
-      if (e.first) val += -0.5 * (2.0 * log(sd) + kLog2Pi);
+      if (need_val) {
+        val = -0.5 * d * d;
+        if (e.first) val += -0.5 * (2.0 * log(sd) + kLog2Pi);
+      }
     } else {  // ACT_PRELU: exponentialLogProb(rate, slopes)
       const double r = fabs((double)hy[b.ha]);
-      val = -r * x + log(r);
+      if (need_val) val = -r * x + log(r);
       grad = -r;
     }
     return;
@@ -175,14 +180,16 @@ __device__ __forceinline__ void prior_elem(const ModelPlan& mp, const Elem& e, c
   const double sc = (double)hy[h0 + 1] * (double)hy[h0 + 1];
   if (b.prior == PRIOR_CAUCHY) {   // +log(1+z^2) - log(pi*gamma)   (BNN_functions.py:51-56, Q1)
     const double z = (x - loc) / sc;
-    val = log1p(z * z) - log(3.14159265358979323846 * sc);
+    if (need_val) val = log1p(z * z) - log(3.14159265358979323846 * sc);
     grad = 2.0 * z / ((1.0 + z * z) * sc);
   } else {                          // multivariateLogProb with scalar sigma (BNN_functions.py:21-32, Q2)
     const double sg = fmin(fmax(sc, 1e-8), 1e8);
     const double d = (x - loc) / sg;
-    val = -0.5 * d * d;
     grad = -d / sg;
-    if (e.first) val += -0.5 * (2.0 * log(sg) + kLog2Pi);
+    if (need_val) {
+      val = -0.5 * d * d;
+      if (e.first) val += -0.5 * (2.0 * log(sg) + kLog2Pi);
+    }
   }
 }
 
@@ -222,7 +229,7 @@ k_finalize(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ pa
       }
       const T th = theta_pad[gi];
       double pg = 0.0;
-      prior_elem<T>(mp, e, hy, (double)th, pv, pg);
+      prior_elem<T>(mp, e, hy, (double)th, pv, pg, logp != nullptr);
       const T gt = (T)(g * scale + pg);
       grad_pad[gi] = gt;
       if (cf.m1 != 0.0 || cf.m2 != 0.0 || cf.m3 != 0.0) {
@@ -329,7 +336,7 @@ k_finalize_split(const __grid_constant__ ModelPlan mp, int S, const T* __restric
       for (int j = 0; j < 8; ++j) g += gs[j][tx];
       const T th = theta_pad[gi];
       double pg = 0.0;
-      prior_elem<T>(mp, e, hy, (double)th, pv, pg);
+      prior_elem<T>(mp, e, hy, (double)th, pv, pg, logp != nullptr);
       const T gt = (T)(g * scale + pg);
       grad_pad[gi] = gt;
       if (cf.m1 != 0.0 || cf.m2 != 0.0 || cf.m3 != 0.0) {
@@ -544,11 +551,13 @@ k_traj_small(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, cons
   cx.Wp = Ws;
   for (int i = tid; i < mp.Ppad; i += NT) Ws[i] = thg[i];
   T p[TRAJ_EPT], gt[TRAJ_EPT];
+  Elem el[TRAJ_EPT];               // what each owned parameter is (decoded once, not once per step)
 #pragma unroll
   for (int k = 0; k < TRAJ_EPT; ++k) {
     const int i = tid + k * NT;
     p[k] = i < mp.Ppad ? mom_pad[(size_t)c * mp.Ppad + i] : T(0);
     gt[k] = T(0);
+    el[k] = decode_elem(mp, i < mp.Ppad ? i : 0);
   }
   load_x_tile<T>(mp, sm + mp.offX, X, 0, (int)N);
   wait_x_tile();
@@ -571,16 +580,17 @@ k_traj_small(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, cons
     // gradient assembly + leapfrog update (k_finalize): step 0 {0.5, 0, 1}, interior {1, 0, 1}, last {1, 0.5, 0}
     const T m1 = j == 0 ? T(0.5) : T(1), m2 = j == L ? T(0.5) : T(0);
     const bool move = j < L;
+    const bool need_val = j == L || (j == 0 && logp_first != nullptr);
     double pv = 0.0;
 #pragma unroll
     for (int k = 0; k < TRAJ_EPT; ++k) {
       const int i = tid + k * NT;
       if (i < mp.Ppad) {
-        const Elem e = decode_elem(mp, i);
+        const Elem e = el[k];
         if (e.kind) {
           const T th = Ws[i];
           double v = 0.0, pg = 0.0;
-          prior_elem<T>(mp, e, hy, (double)th, v, pg);
+          prior_elem<T>(mp, e, hy, (double)th, v, pg, need_val);
           pv += v;
           gt[k] = (T)((double)cx.G[i] * scale + pg);
           p[k] = p[k] + (m1 * eps) * gt[k];
@@ -663,11 +673,13 @@ k_traj_narrow(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, con
     Xs[e] = k < D ? X[(long long)r * D + k] : T(0);
   }
   T p[TRAJ_EPT], gt[TRAJ_EPT];
+  Elem el[TRAJ_EPT];               // what each owned parameter is (decoded once, not once per step)
 #pragma unroll
   for (int k = 0; k < TRAJ_EPT; ++k) {
     const int i = tid + k * NT;
     p[k] = i < mp.Ppad ? mom_pad[(size_t)c * mp.Ppad + i] : T(0);
     gt[k] = T(0);
+    el[k] = decode_elem(mp, i < mp.Ppad ? i : 0);
   }
   double sg = 1.0, scale = 1.0;
   if (mp.lik == LIK_GAUSS) {
@@ -733,16 +745,17 @@ k_traj_narrow(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, con
     // ---- gradient assembly + leapfrog update (k_finalize): step 0 {0.5, 0, 1}, interior {1, 0, 1}, last {1, 0.5, 0}
     const T m1 = j == 0 ? T(0.5) : T(1), m2 = j == L ? T(0.5) : T(0);
     const bool move = j < L;
+    const bool need_val = j == L || (j == 0 && logp_first != nullptr);
     double pv = 0.0;
 #pragma unroll
     for (int k = 0; k < TRAJ_EPT; ++k) {
       const int i = tid + k * NT;
       if (i < mp.Ppad) {
-        const Elem e = decode_elem(mp, i);
+        const Elem e = el[k];
         if (e.kind) {
           const T th = Ws[i];
           double v = 0.0, pg = 0.0;
-          prior_elem<T>(mp, e, hy, (double)th, v, pg);
+          prior_elem<T>(mp, e, hy, (double)th, v, pg, need_val);
           pv += v;
           gt[k] = (T)((double)G[i] * scale + pg);
           p[k] = p[k] + (m1 * eps) * gt[k];
