@@ -576,11 +576,15 @@ k_traj_small(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, cons
     for (int i = tid; i < mp.Ppad; i += NT) cx.G[i] = T(0);
     __syncthreads();
     const T stat = tile_forward_backward<T>(mp, cx, Y, 0, (int)N);
-    const double st = block_sum((double)stat, red);       // barriers inside: G is complete afterwards
+    // the likelihood statistic (and the prior log-density below) only where a log-posterior is reported: the
+    // interior steps need the barrier that completes G, not the fp64 block reductions
+    const bool need_val = j == L || (j == 0 && logp_first != nullptr);
+    double st = 0.0;
+    if (need_val) st = block_sum((double)stat, red);
+    else __syncthreads();
     // gradient assembly + leapfrog update (k_finalize): step 0 {0.5, 0, 1}, interior {1, 0, 1}, last {1, 0.5, 0}
     const T m1 = j == 0 ? T(0.5) : T(1), m2 = j == L ? T(0.5) : T(0);
     const bool move = j < L;
-    const bool need_val = j == L || (j == 0 && logp_first != nullptr);
     double pv = 0.0;
 #pragma unroll
     for (int k = 0; k < TRAJ_EPT; ++k) {
@@ -741,11 +745,15 @@ k_traj_narrow(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, con
       G[b0.pb + o] = sb;
       if (act_has_slopes(b0.act)) G[b0.ps + o] = (b0.act == ACT_SQPRELU ? T(2) * Ws[b0.ps + o] : T(1)) * sc;
     }
-    const double st = block_sum((double)stat, red);       // barriers inside: G is complete afterwards
+    // the likelihood statistic (and the prior log-density below) only where a log-posterior is reported: the
+    // interior steps need the barrier that completes G, not the fp64 block reductions
+    const bool need_val = j == L || (j == 0 && logp_first != nullptr);
+    double st = 0.0;
+    if (need_val) st = block_sum((double)stat, red);
+    else __syncthreads();
     // ---- gradient assembly + leapfrog update (k_finalize): step 0 {0.5, 0, 1}, interior {1, 0, 1}, last {1, 0.5, 0}
     const T m1 = j == 0 ? T(0.5) : T(1), m2 = j == L ? T(0.5) : T(0);
     const bool move = j < L;
-    const bool need_val = j == L || (j == 0 && logp_first != nullptr);
     double pv = 0.0;
 #pragma unroll
     for (int k = 0; k < TRAJ_EPT; ++k) {
