@@ -145,7 +145,7 @@ k_predict_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Pre
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float v = (n < b.out && k + i < b.in) ? src[b.fw + n * b.in + k + i] : 0.f;
-          umma::split_tf32(v, hi[i], lo[i]);
+          umma::split_tf32_trunc(v, hi[i], lo[i]);
         }
         const uint32_t o = umma::core_off(n, k, 128u, cg);
         st4(reinterpret_cast<float*>(wh + o), hi);
@@ -188,7 +188,7 @@ k_predict_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Pre
           for (int i = 0; i < 8; ++i) {
             float a = act_hidden<A>(b0.act, z[i], sl[i]);
             if (A == -1 && c0 + i >= b0.out) a = 0.f;
-            umma::split_tf32(a, h[i], l[i]);
+            umma::split_tf32_trunc(a, h[i], l[i]);
           }
           umma::tmem_st8(umma::tmem_addr(tbase, lane_base, colAh + c0), h);
           umma::tmem_st8(umma::tmem_addr(tbase, lane_base, colAl + c0), l);
@@ -255,7 +255,7 @@ k_predict_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Pre
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) umma::split_tf32(a[i], h[i], lo8[i]);
+            for (int i = 0; i < 8; ++i) umma::split_tf32_trunc(a[i], h[i], lo8[i]);
             umma::tmem_st8(umma::tmem_addr(tbase, lane_base, colAh + c0), h);
             umma::tmem_st8(umma::tmem_addr(tbase, lane_base, colAl + c0), lo8);
           }
