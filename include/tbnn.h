@@ -103,7 +103,10 @@ int tbnn_wide_profile(tbnn_handle* h, const void* theta, long long* clocks_host6
 
 /* Training set resident in HBM (network.py:41-45: tf.constant).  X[N][D] row-major,
  * Y[N][out].  set_data borrows device pointers; set_data_host copies HOST buffers
- * into library-owned device memory on `stream` (the end-to-end path of bench.py). */
+ * into library-owned device memory on `stream` (the end-to-end path of bench.py).
+ * With TBNN_FLAG_UMMA_SWEEP the call also re-lays X into the tcgen05 sweep's core-matrix tiles (a snapshot taken at
+ * this call, on the legacy default stream for tbnn_set_data); the borrowed pointers must stay valid regardless.
+ * tbnn_sweep_info: kernel_kind 0 = tile engine, 1 = phase-serial wide sweep, 2 = FFMA2 wide sweep, 3 = tcgen05 sweep. */
 int tbnn_set_data(tbnn_handle* h, const void* X_dev, const void* Y_dev, int64_t n_rows);
 int tbnn_set_data_host(tbnn_handle* h, const void* X_host, const void* Y_host, int64_t n_rows,
                        void* stream);
