@@ -27,6 +27,9 @@
 #include "kernels.h"
 #include "narrow.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace tbnn {
 
 constexpr int W2_NF = 3;                 // forward warps
@@ -166,9 +169,17 @@ template <int NO, int NB>
 __global__ void __launch_bounds__(W2_THREADS, 1)
 k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restrict__ theta_pad,
               const float* __restrict__ w1p, const float* __restrict__ X, const float* __restrict__ Y,
-              long long N, float* __restrict__ partial, double* __restrict__ stat_part) {
+              long long N, float* __restrict__ partial, double* __restrict__ stat_part, long long* prof) {
   extern __shared__ __align__(16) unsigned char smraw[];
   float* sm = reinterpret_cast<float*>(smraw);
+  // developer aid: clock64 marks of CTA 0, one row of 32 slots per role.  Compiled in only with -DTBNN_W2_PROFILE
+  // (the marks cost ~2 us per sweep); then TBNN_W2_PROF=1 prints the timeline of the fourth launch to stderr.
+#ifdef TBNN_W2_PROFILE
+  if (blockIdx.x != 0 || blockIdx.y != 0) prof = nullptr;
+#define W2_MARK(role, idx) do { if (prof && (idx) < 32) prof[(role) * 32 + (idx)] = clock64(); } while (0)
+#else
+#define W2_MARK(role, idx) do { } while (0)
+#endif
   constexpr int OP = 4 * NO;               // padded outputs of block 0
   constexpr int HO = 2 * NO;               // outputs per forward half
   constexpr int QS = 4 * OP + 4;           // floats per k quad of the pair-interleaved W1 (w1p_quad_stride)
@@ -208,6 +219,7 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
     mbar_fence_init();
   }
   __syncthreads();
+  if (threadIdx.x == 0) W2_MARK(7, 0);
 
   if (warp == W2_NF + W2_NB + W2_NT * W2_NTG + 1) {
     // ================================================================= producer
@@ -225,6 +237,7 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
       float* dst = sm + mp.offX + b * RB * ld0;
       if (lane == 0) {
         fence_proxy_async();
+        W2_MARK(0, p);
         mbar_expect_tx(&full[b], (uint32_t)(R * D * 4));
       }
       __syncwarp();
@@ -243,6 +256,7 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
     for (int p = 0; p < npass; ++p) {
       const int b = p % W2_NBUF;
       mbar_wait(&full[b], (uint32_t)((p / W2_NBUF) & 1));
+      if (warp == 0 && lane == 0) W2_MARK(1, p);
       const float* Xs = sm + mp.offX + b * RB * ld0 + (rg * 4) * ld0;
       u64 acc[4][NO];                        // [row][output pair]: (z[2jp], z[2jp+1]) partial sums
 #pragma unroll
@@ -296,6 +310,7 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
       for (int j = 0; j < HO; j += 2) *reinterpret_cast<float2*>(zo + j) = make_float2(v[j], v[j + 1]);
       __syncwarp();
       if (lane == 0) mbar_arrive(&zready[zb]);
+      if (warp == 0 && lane == 0) W2_MARK(2, p);
     }
   } else if (warp < W2_NF + W2_NB) {
     // ================================================================= B: dW1 in registers
@@ -311,6 +326,7 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
       const uint32_t par = (uint32_t)((p / W2_NBUF) & 1);
       mbar_wait_relaxed(&dzready[b], par);
       mbar_wait(&full[b], par);
+      if (warp == W2_NF && lane == 0) W2_MARK(5, p);
       const int R = ps.size(p);
       if (has) {
         const float* xr = sm + mp.offX + b * RB * ld0 + 4 * bt;
@@ -332,6 +348,7 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[b]);
+      if (warp == W2_NF && lane == 0) W2_MARK(6, p);
     }
     float* out = partial + ((size_t)c * S + s) * mp.Ppad;
     if (bt < (ld0 >> 2)) {
@@ -369,6 +386,7 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
         for (int e = 0; e < 4; ++e)
           yv[i][e] = (act[i] && o0 + e < OUT) ? Y[(r_begin + lo + row0 + i) * (long long)OUT + o0 + e] : 0.f;
       mbar_wait(&zready[zb], (uint32_t)((p >> 1) & 1));
+      if (tw == 0 && lane == 0) W2_MARK(3, p);
       if (p >= 2) mbar_wait(&afree[zb], (uint32_t)(((p >> 1) - 1) & 1));
       // ---- block 0: sum of the F warps' partials, bias, activation
       if (oq < NO && act[0]) {
@@ -502,6 +520,7 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
       }
       if (lane == 0) {
         mbar_arrive(&dzready[b]);
+        if (tw == 0) W2_MARK(4, p);
         mbar_arrive(&tdone[zb]);
       }
     }
@@ -543,7 +562,9 @@ k_sweep_wide2(const __grid_constant__ ModelPlan mp, int S, const float* __restri
     }
     float* out = partial + ((size_t)c * S + s) * mp.Ppad;
     for (int i = b0.pb + lane; i < mp.Ppad; i += 32) out[i] = G[i];
+    if (lane == 0) W2_MARK(7, 1);
   }
+#undef W2_MARK
 }
 
 // ------------------------------------------------------------------ host side
@@ -598,7 +619,27 @@ static void launch_w2(const ModelPlan& wp, dim3 g, size_t smem, const float* the
                       const float* X, const float* Y, long long N, float* partial, double* stat_part,
                       cudaStream_t st) {
   cudaFuncSetAttribute(k_sweep_wide2<NO, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_sweep_wide2<NO, NB><<<g, W2_THREADS, smem, st>>>(wp, (int)g.x, theta_pad, w1p, X, Y, N, partial, stat_part);
+  static const bool want_prof = getenv("TBNN_W2_PROF") != nullptr;
+  static long long* dprof = nullptr;
+  if (want_prof && !dprof) cudaMalloc(&dprof, 8 * 32 * sizeof(long long));
+  if (want_prof) cudaMemsetAsync(dprof, 0, 8 * 32 * sizeof(long long), st);
+  k_sweep_wide2<NO, NB><<<g, W2_THREADS, smem, st>>>(wp, (int)g.x, theta_pad, w1p, X, Y, N, partial, stat_part,
+                                                    want_prof ? dprof : nullptr);
+  if (want_prof) {
+    static int shown = 0;
+    long long h[8 * 32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dprof, sizeof(h), cudaMemcpyDeviceToHost);
+    if (shown++ == 3) {
+      const char* names[8] = {"tma issue", "F tile landed", "F published", "T start", "T done", "B start", "B done", "begin/end A"};
+      const long long t0 = h[7 * 32];
+      for (int r = 0; r < 8; ++r) {
+        fprintf(stderr, "[w2_prof] %-14s", names[r]);
+        for (int i = 0; i < 32; ++i) if (h[r * 32 + i]) fprintf(stderr, " %d:%lld", i, h[r * 32 + i] - t0);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
 }
 
 template <int NO>
