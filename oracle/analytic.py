@@ -11,6 +11,8 @@ import math
 
 import numpy as np
 
+from .tfconst import CLAMP_HI, CLAMP_LO, LOG_2PI_MVLP, f32
+
 LOG_2PI = math.log(2.0 * math.pi)
 DENSE = ("dense", "denseGaussian")
 
@@ -109,14 +111,14 @@ def loglik_and_grad(arch, lik, theta, X, Y, sd_hyper=None):
     sse = None
     dsd = None
     if lik[0] in ("gaussian", "fixed"):
-        sd = sd_hyper ** 2 if lik[0] == "gaussian" else lik[1]
-        sg = min(max(sd, 1e-8), 1e8)
+        sd = sd_hyper ** 2 if lik[0] == "gaussian" else f32(lik[1])     # tf.cast(self.sd, dtype), Q14
+        sg = min(max(sd, CLAMP_LO), CLAMP_HI)
         r = y - f
         sse = float(np.sum(r * r))
-        ll = -0.5 * (2.0 * N * n_out * math.log(sg) + sse / sg ** 2 + N * n_out * LOG_2PI)
+        ll = -0.5 * (2.0 * N * n_out * math.log(sg) + sse / sg ** 2 + N * n_out * LOG_2PI_MVLP)
         df = r / sg ** 2
         if lik[0] == "gaussian":
-            inside = 1e-8 <= sd <= 1e8
+            inside = CLAMP_LO <= sd <= CLAMP_HI
             dll_dsg = -(N * n_out) / sg + sse / sg ** 3
             dsd = (dll_dsg if inside else 0.0) * 2.0 * sd_hyper
     else:
@@ -162,14 +164,14 @@ def _prior_terms(it, theta, hyper, want_hyper_grad):
         for (off, n, hm, hs) in ((it["w"], it["o"] * it["i"], 0, 1), (it["b"], it["o"], 2, 3)):
             x = theta[off:off + n]
             s = h[hs] ** 2
-            sg = min(max(s, 1e-8), 1e8)
+            sg = min(max(s, CLAMP_LO), CLAMP_HI)
             d = x - h[hm]
             ss = np.sum(d * d)
-            val += -0.5 * (2.0 * math.log(sg) + ss / sg ** 2 + LOG_2PI)
+            val += -0.5 * (2.0 * math.log(sg) + ss / sg ** 2 + LOG_2PI_MVLP)
             dth.append((off, -d / sg ** 2))
             if want_hyper_grad:
                 dh[it["h"] + hm] = np.sum(d) / sg ** 2
-                inside = 1e-8 <= s <= 1e8
+                inside = CLAMP_LO <= s <= CLAMP_HI
                 dh[it["h"] + hs] = ((-1.0 / sg + ss / sg ** 3) if inside else 0.0) * 2.0 * h[hs]
         return val, dth, dh
     raise ValueError(k)
@@ -190,8 +192,8 @@ def main_value_and_grad(arch, lik, theta, hyper, X, Y):
         elif k == "squareprelu":                   # Q4 "as written": prior on the un-squared slope
             a = theta[it["s"]:it["s"] + it["n"]]
             mean, sd = hyper[it["h"]], hyper[it["h"] + 1]
-            sg = min(max(sd, 1e-8), 1e8)
-            val += -0.5 * (2.0 * math.log(sg) + np.sum(((a - mean) / sg) ** 2) + LOG_2PI)
+            sg = min(max(sd, CLAMP_LO), CLAMP_HI)
+            val += -0.5 * (2.0 * math.log(sg) + np.sum(((a - mean) / sg) ** 2) + LOG_2PI_MVLP)
             grad[it["s"]:it["s"] + it["n"]] += -(a - mean) / sg ** 2
         elif k == "prelu":
             a = theta[it["s"]:it["s"] + it["n"]]
@@ -210,6 +212,7 @@ def hyper_value_and_grad(arch, lik, theta, hyper, X, Y, sse=None):
     val = 0.0
 
     def logn(v, m, s):
+        m, s = f32(m), f32(s)                       # float32 hyper-prior constants (Q14)
         return -0.5 * ((v - m) / s) ** 2 - math.log(s) - 0.5 * LOG_2PI
 
     for it in items:
@@ -221,9 +224,9 @@ def hyper_value_and_grad(arch, lik, theta, hyper, X, Y, sse=None):
             for idx, d in dh.items():
                 g[idx] += d
             if k == "dense":
-                loc, sc, lm, ls = 0.0, 0.2, 0.5 ** 0.5, 0.5
+                loc, sc, lm, ls = 0.0, f32(0.2), f32(0.5 ** 0.5), 0.5
             else:
-                loc, sc, lm, ls = 0.0, 0.1, 1.0, 0.1
+                loc, sc, lm, ls = 0.0, f32(0.1), 1.0, f32(0.1)
             for j in (0, 2):
                 val += logn(hyper[o + j], loc, sc)
                 g[o + j] += -(hyper[o + j] - loc) / sc ** 2
@@ -234,30 +237,30 @@ def hyper_value_and_grad(arch, lik, theta, hyper, X, Y, sse=None):
         elif k == "squareprelu":
             a2 = theta[it["s"]:it["s"] + it["n"]] ** 2
             mean, sd = hyper[o], hyper[o + 1]
-            sg = min(max(sd, 1e-8), 1e8)
+            sg = min(max(sd, CLAMP_LO), CLAMP_HI)
             d = a2 - mean
             ss = np.sum(d * d)
-            val += -0.5 * (2.0 * math.log(sg) + ss / sg ** 2 + LOG_2PI)
+            val += -0.5 * (2.0 * math.log(sg) + ss / sg ** 2 + LOG_2PI_MVLP)
             val += logn(mean, 0.0, 0.3) + logn(sd, 0.3, 0.1)
-            g[o] += np.sum(d) / sg ** 2 - mean / 0.3 ** 2
-            inside = 1e-8 <= sd <= 1e8
-            g[o + 1] += ((-1.0 / sg + ss / sg ** 3) if inside else 0.0) - (sd - 0.3) / 0.1 ** 2
+            g[o] += np.sum(d) / sg ** 2 - mean / f32(0.3) ** 2
+            inside = CLAMP_LO <= sd <= CLAMP_HI
+            g[o + 1] += ((-1.0 / sg + ss / sg ** 3) if inside else 0.0) - (sd - f32(0.3)) / f32(0.1) ** 2
         elif k == "prelu":
             a = np.abs(theta[it["s"]:it["s"] + it["n"]])
             r = hyper[o]
             ar = abs(r)
             sgn = 1.0 if r > 0 else (-1.0 if r < 0 else 0.0)
-            val += -0.3 * r + math.log(0.3)
+            val += -f32(0.3) * r + math.log(f32(0.3))
             val += np.sum(-ar * a) + it["n"] * math.log(ar)
-            g[o] += -0.3 + sgn * (-np.sum(a) + it["n"] / ar)
+            g[o] += -f32(0.3) + sgn * (-np.sum(a) + it["n"] / ar)
     if lik[0] == "gaussian":
         sdh = hyper[-1]
         sd = sdh ** 2
-        sg = min(max(sd, 1e-8), 1e8)
+        sg = min(max(sd, CLAMP_LO), CLAMP_HI)
         if sse is None:
             _, _, sse, _ = loglik_and_grad(arch, lik, theta, X, Y, sdh)
         n = np.asarray(Y).size
-        val += -0.5 * (2.0 * n * math.log(sg) + sse / sg ** 2 + n * LOG_2PI)
-        inside = 1e-8 <= sd <= 1e8
+        val += -0.5 * (2.0 * n * math.log(sg) + sse / sg ** 2 + n * LOG_2PI_MVLP)
+        inside = CLAMP_LO <= sd <= CLAMP_HI
         g[-1] += ((-n / sg + sse / sg ** 3) if inside else 0.0) * 2.0 * sdh
     return float(val), g

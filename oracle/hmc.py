@@ -10,9 +10,11 @@ All functions work on flat torch vectors in the dtype of ``theta``.
 """
 import math
 
+import numpy as np
 import torch
 
 from . import targets
+from .tfconst import f32
 
 
 def leapfrog(value_and_grad, theta, momentum, eps, L, logp0=None, grad0=None):
@@ -67,7 +69,9 @@ def dual_averaging(epoch, accept, h, log_eps_bar, step, hyper_step0, burnin,
     """network.py:457-469 with the constants of :241-248.  ``epoch`` is the
     0-based iteration; mu = log(100*hyperStepSize)."""
     m = epoch + 1.0
-    mu = math.log(100.0 * hyper_step0)
+    # tf.cast(0.4, dtype) and tf.cast(tf.math.log(100*hyperStepSize), dtype) pass through float32 (Q14, oracle/tfconst.py)
+    gamma = f32(gamma)
+    mu = float(np.log(np.float32(100.0 * hyper_step0)))
     h = (1 - 1 / (m + t0)) * h + (1 / (m + t0)) * (target - accept)
     log_eps = mu - h * (m ** 0.5) / gamma
     log_eps_bar = (1 - m ** (-kappa)) * log_eps_bar + m ** (-kappa) * log_eps

@@ -20,6 +20,8 @@ import math
 
 import torch
 
+from .tfconst import CLAMP_HI, CLAMP_LO, LOG_2PI_MVLP, f32
+
 DENSE_KINDS = ("dense", "denseGaussian")
 PARAM_ACTS = ("prelu", "squareprelu")
 PLAIN_ACTS = ("relu", "tanh", "sigmoid", "Exp", "elu", "leakyrelu", "softmax")
@@ -112,11 +114,11 @@ def multivariate_log_prob(sigma, mu, x):
     k*log(2pi) term count the elements OF SIGMA (scalar sigma => once, Q2)."""
     dt = x.dtype
     sigma = torch.as_tensor(sigma, dtype=dt)
-    sigma = torch.clamp(sigma, min=1e-8, max=1e8)
+    sigma = torch.clamp(sigma, min=CLAMP_LO, max=CLAMP_HI)    # tf.cast(10**-8, dtype): float32-rounded (Q14)
     log_det = 2.0 * torch.sum(torch.log(sigma))
     k = float(sigma.numel())
     dif = (1.0 / sigma) * (x - mu)
-    return -0.5 * (log_det + torch.sum(dif * dif) + k * LOG_2PI)
+    return -0.5 * (log_det + torch.sum(dif * dif) + k * LOG_2PI_MVLP)
 
 
 def cauchy_log_prob(gamma, x0, x):
@@ -126,7 +128,9 @@ def cauchy_log_prob(gamma, x0, x):
 
 
 def log_normal_1d(v, m, s):
-    """tfd.MultivariateNormalDiag(loc=[m], scale_diag=[s]).log_prob([v])."""
+    """tfd.MultivariateNormalDiag(loc=[m], scale_diag=[s]).log_prob([v]); loc and scale are python lists,
+    i.e. float32 constants (Q14)."""
+    m, s = f32(m), f32(s)
     return -0.5 * ((v - m) / s) ** 2 - math.log(s) - 0.5 * LOG_2PI
 
 
@@ -192,7 +196,7 @@ def log_likelihood(arch, lik, theta, X, Y, sd_hyper=None):
     dt = f.dtype
     if lik[0] in ("gaussian", "fixed"):
         cur = f.t()
-        sd = sd_hyper ** 2 if lik[0] == "gaussian" else torch.tensor(lik[1], dtype=dt)
+        sd = sd_hyper ** 2 if lik[0] == "gaussian" else torch.tensor(f32(lik[1]), dtype=dt)   # tf.cast(self.sd, dtype)
         sigma = torch.ones_like(cur) * sd
         real = Y.reshape(cur.shape)
         return multivariate_log_prob(sigma, cur, real)
@@ -251,7 +255,7 @@ def layer_hyper_prob(layer, hypers, tensors):
                 + log_normal_1d(hypers[0], 0.0, 0.3) + log_normal_1d(hypers[1], 0.3, 0.1))
     if k == "prelu":
         dt = tensors[0].dtype
-        return (exponential_log_prob(torch.tensor(0.3, dtype=dt), hypers[0])
+        return (exponential_log_prob(torch.tensor(f32(0.3), dtype=dt), hypers[0])
                 + torch.sum(exponential_log_prob(hypers[0], torch.abs(tensors[0]))))
     raise ValueError(k)
 

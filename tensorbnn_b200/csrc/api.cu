@@ -185,7 +185,7 @@ static int plan_structure(const tbnn_desc* d, ModelPlan& mp) {
   mp.P = fcur; mp.Ppad = pcur;
   mp.lik = d->likelihood == TBNN_LIK_GAUSSIAN ? LIK_GAUSS
            : d->likelihood == TBNN_LIK_FIXED_GAUSSIAN ? LIK_FIXED : LIK_BERN;
-  mp.fixed_sd = d->fixed_sd;
+  mp.fixed_sd = (double)(float)d->fixed_sd;   // tf.cast(self.sd, dtype), likelihood.py:161 (Q14)
   mp.lik_h = mp.lik == LIK_GAUSS ? hcur++ : -1;
   mp.H = hcur;
   if (mp.H > 8 * MAXB) return fail("too many hyper parameters");

@@ -87,7 +87,7 @@ __device__ double hyper_eval_dev(const ModelPlan& mp, const T* __restrict__ th, 
   }
   __syncthreads();
   // ---- per-block value and gradient (thread l handles block l; thread nb the likelihood)
-  const double kLog2Pi = 1.8378770664093453, kPi = 3.14159265358979323846;
+  const double kLog2Pi = tfc::kLog2PiCast, kPi = 3.14159265358979323846;
   if (threadIdx.x < mp.nb) {
     const int l = threadIdx.x;
     const BlockPlan& b = mp.b[l];
@@ -99,43 +99,43 @@ __device__ double hyper_eval_dev(const ModelPlan& mp, const T* __restrict__ th, 
       const double n = t == 0 ? (double)b.out * b.in : (double)b.out;
       if (b.prior == PRIOR_CAUCHY) {
         val += s[0] - n * log(kPi * sc);
-        val += logn(loc, 0.0, 0.2) + logn(sc, 0.70710678118654757, 0.5);      // layer.py:136-153
-        sh.g[i0] = -s[1] / sc - loc / (0.2 * 0.2);
-        sh.g[i1] = ((-s[2] / sc - n / sc) - (sc - 0.70710678118654757) / (0.5 * 0.5)) * 2.0 * h;
+        val += logn(loc, 0.0, tfc::k0p2) + logn(sc, tfc::kSqrtHalf, 0.5);      // layer.py:136-153
+        sh.g[i0] = -s[1] / sc - loc / (tfc::k0p2 * tfc::k0p2);
+        sh.g[i1] = ((-s[2] / sc - n / sc) - (sc - tfc::kSqrtHalf) / (0.5 * 0.5)) * 2.0 * h;
       } else {
-        const double sg = fmin(fmax(sc, 1e-8), 1e8);
-        const bool inside = sc >= 1e-8 && sc <= 1e8;
+        const double sg = fmin(fmax(sc, tfc::kClampLo), tfc::kClampHi);
+        const bool inside = sc >= tfc::kClampLo && sc <= tfc::kClampHi;
         val += -0.5 * (2.0 * log(sg) + s[0] / (sg * sg) + kLog2Pi);
-        val += logn(loc, 0.0, 0.1) + logn(sc, 1.0, 0.1);                      // layer.py:317-334
-        sh.g[i0] = s[1] / (sg * sg) - loc / (0.1 * 0.1);
-        sh.g[i1] = ((inside ? (-1.0 / sg + s[0] / (sg * sg * sg)) : 0.0) - (sc - 1.0) / (0.1 * 0.1)) *
+        val += logn(loc, 0.0, tfc::k0p1) + logn(sc, 1.0, tfc::k0p1);                      // layer.py:317-334
+        sh.g[i0] = s[1] / (sg * sg) - loc / (tfc::k0p1 * tfc::k0p1);
+        sh.g[i1] = ((inside ? (-1.0 / sg + s[0] / (sg * sg * sg)) : 0.0) - (sc - 1.0) / (tfc::k0p1 * tfc::k0p1)) *
                    2.0 * h;
       }
     }
     if (b.act == ACT_SQPRELU) {                       // activationFunctions.py:365-380
       const double* s = &sh.sums[(l * 3 + 2) * 3];
       const double mean = hv[b.ha], sd = hv[b.ha + 1];
-      const double sg = fmin(fmax(sd, 1e-8), 1e8);
-      const bool inside = sd >= 1e-8 && sd <= 1e8;
+      const double sg = fmin(fmax(sd, tfc::kClampLo), tfc::kClampHi);
+      const bool inside = sd >= tfc::kClampLo && sd <= tfc::kClampHi;
       val += -0.5 * (2.0 * log(sg) + s[0] / (sg * sg) + kLog2Pi);
-      val += logn(mean, 0.0, 0.3) + logn(sd, 0.3, 0.1);
-      sh.g[b.ha] = s[1] / (sg * sg) - mean / (0.3 * 0.3);
-      sh.g[b.ha + 1] = (inside ? (-1.0 / sg + s[0] / (sg * sg * sg)) : 0.0) - (sd - 0.3) / (0.1 * 0.1);
+      val += logn(mean, 0.0, tfc::k0p3) + logn(sd, tfc::k0p3, tfc::k0p1);
+      sh.g[b.ha] = s[1] / (sg * sg) - mean / (tfc::k0p3 * tfc::k0p3);
+      sh.g[b.ha + 1] = (inside ? (-1.0 / sg + s[0] / (sg * sg * sg)) : 0.0) - (sd - tfc::k0p3) / (tfc::k0p1 * tfc::k0p1);
     } else if (b.act == ACT_PRELU) {                  // activationFunctions.py:209-218
       const double* s = &sh.sums[(l * 3 + 2) * 3];
       const double r = hv[b.ha], ar = fabs(r), n = (double)b.out;
       const double sgn = r > 0 ? 1.0 : (r < 0 ? -1.0 : 0.0);
-      val += -0.3 * r + log(0.3);
+      val += -tfc::k0p3 * r + log(tfc::k0p3);
       val += -ar * s[0] + n * log(ar);
-      sh.g[b.ha] = -0.3 + sgn * (-s[0] + n / ar);
+      sh.g[b.ha] = -tfc::k0p3 + sgn * (-s[0] + n / ar);
     }
     sh.part[l] = val;
   } else if (threadIdx.x == mp.nb) {
     double val = 0.0;
     if (mp.lik == LIK_GAUSS) {                        // likelihood.py:88-94 with sd = argv[-1]
       const double h = hv[mp.lik_h], sd = h * h;
-      const double sg = fmin(fmax(sd, 1e-8), 1e8);
-      const bool inside = sd >= 1e-8 && sd <= 1e8;
+      const double sg = fmin(fmax(sd, tfc::kClampLo), tfc::kClampHi);
+      const bool inside = sd >= tfc::kClampLo && sd <= tfc::kClampHi;
       const double n = (double)Ntot * (double)mp.OUT;
       val = -0.5 * (2.0 * n * log(sg) + sse / (sg * sg) + n * kLog2Pi);
       sh.g[mp.lik_h] = (inside ? (-n / sg + sse / (sg * sg * sg)) : 0.0) * 2.0 * h;
@@ -222,8 +222,8 @@ k_hyper_step(const __grid_constant__ ModelPlan mp, const T* __restrict__ theta_f
     acc_s = (log(u) < lar) ? 1 : 0;
     const double accept = lar < 0.0 ? exp(lar) : 1.0;
     // dual averaging, network.py:457-469 (constants :241-248)
-    const double target = 0.95, gamma = 0.4, t0 = 10.0, kappa = 0.75;
-    const double m = epoch + 1.0, mu = log(100.0 * hyper_step0);
+    const double target = 0.95, gamma = tfc::k0p4, t0 = 10.0, kappa = 0.75;
+    const double m = epoch + 1.0, mu = (double)logf((float)(100.0 * hyper_step0));   // tf.math.log of a python float: float32
     double hda = (double)da_state[c * 3 + 0], leb = (double)da_state[c * 3 + 1];
     hda = (1.0 - 1.0 / (m + t0)) * hda + (1.0 / (m + t0)) * (target - accept);
     const double logEps = mu - hda * sqrt(m) / gamma;

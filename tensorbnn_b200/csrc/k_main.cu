@@ -155,13 +155,13 @@ __device__ __forceinline__ void prior_elem(const ModelPlan& mp, const Elem& e, c
   // need_val = false: gradient only (interior leapfrog steps never read the log-density; its fp64 log / log1p
   // are most of the cost of this function)
   const BlockPlan& b = mp.b[e.blk];
-  const double kLog2Pi = 1.8378770664093453;
+  const double kLog2Pi = tfc::kLog2PiCast;
   val = 0.0;
   if (e.kind == 3) {
     if (b.act == ACT_SQPRELU) {
       const double mean = (double)hy[b.ha];
       double sd = (double)hy[b.ha + 1];
-      sd = fmin(fmax(sd, 1e-8), 1e8);
+      sd = fmin(fmax(sd, tfc::kClampLo), tfc::kClampHi);
       const double d = (x - mean) / sd;
       grad = -d / sd;
       if (need_val) {
@@ -183,7 +183,7 @@ __device__ __forceinline__ void prior_elem(const ModelPlan& mp, const Elem& e, c
     if (need_val) val = log1p(z * z) - log(3.14159265358979323846 * sc);
     grad = 2.0 * z / ((1.0 + z * z) * sc);
   } else {                          // multivariateLogProb with scalar sigma (BNN_functions.py:21-32, Q2)
-    const double sg = fmin(fmax(sc, 1e-8), 1e8);
+    const double sg = fmin(fmax(sc, tfc::kClampLo), tfc::kClampHi);
     const double d = (x - loc) / sg;
     grad = -d / sg;
     if (need_val) {
@@ -210,10 +210,10 @@ k_finalize(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ pa
   double sg = 1.0, scale = 1.0;
   if (mp.lik == LIK_GAUSS) {
     const double h = (double)hy[mp.lik_h];
-    sg = fmin(fmax(h * h, 1e-8), 1e8);
+    sg = fmin(fmax(h * h, tfc::kClampLo), tfc::kClampHi);
     scale = 1.0 / (sg * sg);
   } else if (mp.lik == LIK_FIXED) {
-    sg = fmin(fmax(mp.fixed_sd, 1e-8), 1e8);
+    sg = fmin(fmax(mp.fixed_sd, tfc::kClampLo), tfc::kClampHi);
     scale = 1.0 / (sg * sg);
   }
   double pv = 0.0;
@@ -275,7 +275,7 @@ k_finalize(const __grid_constant__ ModelPlan mp, int S, const T* __restrict__ pa
       ll = st;
     } else {
       const double n = (double)Ntot * (double)mp.OUT;
-      ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * 1.8378770664093453);
+      ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * tfc::kLog2PiCast);
     }
     logp[c] = prior + ll;
     if (stat_out) stat_out[c] = st;
@@ -320,10 +320,10 @@ k_finalize_split(const __grid_constant__ ModelPlan mp, int S, const T* __restric
   double sg = 1.0, scale = 1.0;
   if (mp.lik == LIK_GAUSS) {
     const double h = (double)hy[mp.lik_h];
-    sg = fmin(fmax(h * h, 1e-8), 1e8);
+    sg = fmin(fmax(h * h, tfc::kClampLo), tfc::kClampHi);
     scale = 1.0 / (sg * sg);
   } else if (mp.lik == LIK_FIXED) {
-    sg = fmin(fmax(mp.fixed_sd, 1e-8), 1e8);
+    sg = fmin(fmax(mp.fixed_sd, tfc::kClampLo), tfc::kClampHi);
     scale = 1.0 / (sg * sg);
   }
   double pv = 0.0;
@@ -381,7 +381,7 @@ k_finalize_split(const __grid_constant__ ModelPlan mp, int S, const T* __restric
       ll = st;
     } else {
       const double n = (double)Ntot * (double)mp.OUT;
-      ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * 1.8378770664093453);
+      ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * tfc::kLog2PiCast);
     }
     logp[c] = prior + ll;
     if (stat_out) stat_out[c] = st;
@@ -564,10 +564,10 @@ k_traj_small(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, cons
   double sg = 1.0, scale = 1.0;
   if (mp.lik == LIK_GAUSS) {
     const double h = (double)hy[mp.lik_h];
-    sg = fmin(fmax(h * h, 1e-8), 1e8);
+    sg = fmin(fmax(h * h, tfc::kClampLo), tfc::kClampHi);
     scale = 1.0 / (sg * sg);
   } else if (mp.lik == LIK_FIXED) {
-    sg = fmin(fmax(mp.fixed_sd, 1e-8), 1e8);
+    sg = fmin(fmax(mp.fixed_sd, tfc::kClampLo), tfc::kClampHi);
     scale = 1.0 / (sg * sg);
   }
   const T eps = eps_dev[c];
@@ -614,7 +614,7 @@ k_traj_small(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, cons
           ll = st;
         } else {
           const double n = (double)Ntot * (double)mp.OUT;
-          ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * 1.8378770664093453);
+          ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * tfc::kLog2PiCast);
         }
         if (j == L) { logp_last[c] = prior + ll; if (stat_last) stat_last[c] = st; }
         else { logp_first[c] = prior + ll; if (stat_first) stat_first[c] = st; }
@@ -688,10 +688,10 @@ k_traj_narrow(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, con
   double sg = 1.0, scale = 1.0;
   if (mp.lik == LIK_GAUSS) {
     const double h = (double)hy[mp.lik_h];
-    sg = fmin(fmax(h * h, 1e-8), 1e8);
+    sg = fmin(fmax(h * h, tfc::kClampLo), tfc::kClampHi);
     scale = 1.0 / (sg * sg);
   } else if (mp.lik == LIK_FIXED) {
-    sg = fmin(fmax(mp.fixed_sd, 1e-8), 1e8);
+    sg = fmin(fmax(mp.fixed_sd, tfc::kClampLo), tfc::kClampHi);
     scale = 1.0 / (sg * sg);
   }
   const T eps = eps_dev[c];
@@ -783,7 +783,7 @@ k_traj_narrow(const __grid_constant__ ModelPlan mp, const T* __restrict__ X, con
           ll = st;
         } else {
           const double n = (double)Ntot * (double)mp.OUT;
-          ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * 1.8378770664093453);
+          ll = -0.5 * (2.0 * n * log(sg) + st * scale + n * tfc::kLog2PiCast);
         }
         if (j == L) { logp_last[c] = prior + ll; if (stat_last) stat_last[c] = st; }
         else { logp_first[c] = prior + ll; if (stat_first) stat_first[c] = st; }

@@ -63,3 +63,19 @@ struct ModelPlan {
 };
 
 }  // namespace tbnn
+
+// Constants exactly as TensorFlow materialises them in the reference (quirk Q14):
+// tf.cast(python_float, dtype) converts to a float32 tensor FIRST, so 2*pi and the 1e-8 clamp of
+// multivariateLogProb (BNN_functions.py:23-24,30), FixedGaussianLikelihood's sd (likelihood.py:161), the
+// hyper-prior locations/scales (layer.py:137-153,318-334; activationFunctions.py:144-145,301-306: float32
+// distributions) and the dual-averaging constants (network.py:241-248) carry float32 rounding even in a
+// float64 network.  Invisible in float32; needed for 1e-10 agreement with the reference's arithmetic in fp64.
+namespace tfc {
+constexpr double kLog2PiCast = 1.8378770942368803;    // log((double)(float)(2*pi)): k*log(2pi) of multivariateLogProb
+constexpr double kLog2Pi = 1.8378770664093453;        // exact: inside tfd.MultivariateNormalDiag.log_prob
+constexpr double kClampLo = (double)1e-8f;            // 9.99999993922529e-09
+constexpr double kClampHi = 1e8;
+constexpr double k0p1 = (double)0.1f, k0p2 = (double)0.2f, k0p3 = (double)0.3f, k0p4 = (double)0.4f;
+constexpr double kSqrtHalf = (double)0.70710678118654757f;   // 0.5**0.5 -> float32
+}  // namespace tfc
+

@@ -52,10 +52,11 @@ def test_hmc_step_accept_reject_and_safe_sum():
 
 
 def test_dual_averaging_constants():
-    """network.py:457-469 by hand for the first epoch: m=1, t0=10, gamma=.4, kappa=.75, target=.95."""
+    """network.py:457-469 by hand for the first epoch: m=1, t0=10, gamma=.4, kappa=.75, target=.95
+    (gamma and mu are tf.cast(python float) values, i.e. float32-rounded: oracle/tfconst.py, Q14)."""
     h, leb, st = hmc.dual_averaging(0.0, 0.5, 0.0, 0.0, 1e-2, 1e-2, 1000)
     h_ref = (1 / 11) * (0.95 - 0.5)
-    le = math.log(100 * 1e-2) - h_ref * 1.0 / 0.4
+    le = float(np.log(np.float32(100 * 1e-2))) - h_ref * 1.0 / float(np.float32(0.4))
     assert abs(h - h_ref) < 1e-15 and abs(leb - le) < 1e-15 and abs(st - math.exp(le)) < 1e-15
     # frozen after 0.8 * burnin
     _, _, st2 = hmc.dual_averaging(900.0, 0.5, 0.1, -3.0, 7e-3, 1e-2, 1000)

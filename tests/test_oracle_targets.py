@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import analytic, targets
+from oracle import tfconst, analytic, targets
 from tensorbnn_b200 import workloads as wl
 
 torch.set_default_dtype(torch.float64)
@@ -98,9 +98,11 @@ def test_known_answer_zero_weights_c1():
     hyper = wl.init_hyper(arch, lik)
     lp, _ = analytic.main_value_and_grad(arch, lik, theta, hyper, cfg["X"], cfg["Y"])
     y = cfg["Y"]
-    ll = -0.5 * (2 * 11 * math.log(0.1) + np.sum(y ** 2) / 0.01 + 11 * math.log(2 * math.pi))
+    # constants as TensorFlow materialises them (tf.cast of a python float goes through float32: oracle/tfconst.py, Q14)
+    sd, log2pi = tfconst.f32(0.1), tfconst.LOG_2PI_MVLP
+    ll = -0.5 * (2 * 11 * math.log(sd) + np.sum(y ** 2) / sd ** 2 + 11 * log2pi)
     # 4 Gaussian dense layers x (W,b), sigma=1, mu=0, all-zero tensors: -0.5*log(2pi) each (Q2)
-    prior = 8 * (-0.5 * math.log(2 * math.pi))
+    prior = 8 * (-0.5 * log2pi)
     assert abs(lp - (ll + prior)) < 1e-10
     lp_t, _ = targets.main_value_and_grad(arch, lik, torch.tensor(theta), torch.tensor(hyper),
                                           torch.tensor(cfg["X"]), torch.tensor(cfg["Y"]))
@@ -119,11 +121,11 @@ def test_known_answer_single_dense_n1():
     y = np.array([1.0])
     hy = wl.init_hyper(arch, ("fixed", 0.5))
     lp, _ = analytic.main_value_and_grad(arch, ("fixed", 0.5), theta, hy, X, y)
-    ll = -0.5 * (2 * math.log(0.5) + ((1.0 - f) / 0.5) ** 2 + math.log(2 * math.pi))
+    ll = -0.5 * (2 * math.log(0.5) + ((1.0 - f) / 0.5) ** 2 + tfconst.LOG_2PI_MVLP)
     assert abs(lp - (prior + ll)) < 1e-12
     hy = wl.init_hyper(arch, ("gaussian", 0.09))                     # hyper = 0.3, sigma = 0.09
     lp, _ = analytic.main_value_and_grad(arch, ("gaussian", 0.09), theta, hy, X, y)
-    ll = -0.5 * (2 * math.log(0.09) + ((1.0 - f) / 0.09) ** 2 + math.log(2 * math.pi))
+    ll = -0.5 * (2 * math.log(0.09) + ((1.0 - f) / 0.09) ** 2 + tfconst.LOG_2PI_MVLP)
     assert abs(lp - (prior + ll)) < 1e-9
     arch_b = [("dense", 1, 1), ("sigmoid",)]
     hy = wl.init_hyper(arch_b, ("bernoulli",))
@@ -156,7 +158,8 @@ def test_clip_and_clamp_edges():
     # sigma clamp: multivariateLogProb with sigma below 1e-8 uses 1e-8 and has zero sigma-gradient
     s = torch.tensor(1e-12, requires_grad=True)
     v = targets.multivariate_log_prob(s, 0.0, torch.tensor([1e-9]))
-    expect = -0.5 * (2 * math.log(1e-8) + (1e-9 / 1e-8) ** 2 + math.log(2 * math.pi))
+    lo = tfconst.CLAMP_LO
+    expect = -0.5 * (2 * math.log(lo) + (1e-9 / lo) ** 2 + tfconst.LOG_2PI_MVLP)
     assert abs(v.item() - expect) < 1e-9
     v.backward()
     assert s.grad.item() == 0.0
