@@ -59,7 +59,9 @@ enum { TBNN_FLAG_NO_WIDE = 1,  /* never use the wide-first-layer row sweeps */
        TBNN_FLAG_UMMA_SWEEP = 8, /* wide-first-layer row sweep on tcgen05 (3xTF32, k_sweep_umma) instead of FP32 FFMA2:
                                     correct to ~1e-6 but not yet faster (profiles/r1d_summary.md), so opt-in */
        TBNN_FLAG_NO_PERSISTENT = 16, /* never run a trajectory as one persistent launch (k_traj_small / k_traj_narrow) */
-       TBNN_FLAG_NO_NARROW = 32 /* persistent trajectories on the tile engine only (k_traj_small), not k_traj_narrow */ };
+       TBNN_FLAG_NO_NARROW = 32, /* persistent trajectories on the tile engine only (k_traj_small), not k_traj_narrow */
+       TBNN_FLAG_NO_UMMA_TRAIN = 64 /* hidden-layer GEMMs of the training sweep on FP32 FFMA (k_partial) instead of
+                                       tcgen05 3xTF32 (k_train_umma) */ };
 
 typedef struct {
   int32_t kind;    /* TBNN_DENSE_* or TBNN_ACT_* */

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtbnn.so")
-SOURCES = ["api.cu", "k_main.cu", "k_wide.cu", "k_wide2.cu", "k_sweep_umma.cu", "k_hyper.cu", "k_predict.cu", "k_predict_umma.cu", "k_adapter.cu"]
+SOURCES = ["api.cu", "k_main.cu", "k_wide.cu", "k_wide2.cu", "k_sweep_umma.cu", "k_train_umma.cu", "k_hyper.cu", "k_predict.cu", "k_predict_umma.cu", "k_adapter.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

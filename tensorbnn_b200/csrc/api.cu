@@ -74,6 +74,11 @@ struct tbnn_handle {
   bool use_usweep = false;         // ... and planned for the current data (after_data)
   ModelPlan uw;                    // its tail plan
   USweepPlan up;
+  bool use_tu = false;             // tcgen05 training sweep (k_train_umma) planned for this network / dtype / flags
+  TrainUmmaPlan tu;
+  void* tu_wimg = nullptr;         // per-chain weight operand images (owned)
+  void* tu_scratch = nullptr;      // per-CTA pre-activation scratch (owned)
+  int S_tu = 1;                    // CTAs per chain of that sweep (128-row tiles)
   void* Xt = nullptr;              // training matrix in core-matrix tiles (owned)
   size_t Xt_cap = 0;
   // CUDA graphs of 2^k interior leapfrog steps (sweep + finalize each), replayed instead of 2 * 2^k launches;
@@ -336,11 +341,17 @@ extern "C" int tbnn_create(const tbnn_desc* d, tbnn_handle** out) {
   h->use_umma_predict = d->dtype == TBNN_F32 && !(d->flags & TBNN_FLAG_NO_UMMA) && predict_umma_supported(h->mp);
   h->want_usweep = d->dtype == TBNN_F32 && (d->flags & TBNN_FLAG_UMMA_SWEEP) && !(d->flags & (TBNN_FLAG_NO_WIDE | TBNN_FLAG_NO_UMMA)) &&
                    usweep_supported(h->mp);
+  h->use_tu = d->dtype == TBNN_F32 && !(d->flags & (TBNN_FLAG_NO_UMMA | TBNN_FLAG_NO_UMMA_TRAIN)) && !h->use_wide &&
+              plan_train_umma(h->mp, h->tu, SMEM_LIMIT);
   if (plan_predict(h)) h->pp_rows = 0;   // predictor unavailable for this network/dtype; tbnn_predict reports it
   const ModelPlan& mp = h->mp;
   const size_t C = h->C, e = h->esz, pp = (size_t)mp.Ppad;
   h->nblkF = (mp.Ppad + 31) / 32;   // enough for both finalize variants
   if (h->use_wide2) CU(cudaMalloc(&h->w1p, C * (size_t)w1p_elems(h->mp) * sizeof(float)));
+  if (h->use_tu) {
+    CU(cudaMalloc(&h->tu_wimg, train_umma_wimg_bytes(h->tu, h->C)));
+    CU(cudaMalloc(&h->tu_scratch, train_umma_scratch_bytes(h->tu, h->num_sms)));
+  }
   CU(cudaMalloc(&h->theta_pad, C * pp * e));
   CU(cudaMalloc(&h->theta0_pad, C * pp * e));
   CU(cudaMalloc(&h->mom_pad, C * pp * e));
@@ -363,7 +374,7 @@ extern "C" int tbnn_destroy(tbnn_handle* h) {
   cudaSetDevice(h->device);
   void* ptrs[] = {h->theta_pad, h->theta0_pad, h->mom_pad, h->grad_pad, h->gsum, h->eps_dev, h->flat_tmp,
                   h->small_T, h->prior_part, h->dbl, h->ticket, h->partial, h->stat_part, h->X_own,
-                  h->Y_own, h->pred_ws, h->w1p, h->Xt};
+                  h->Y_own, h->pred_ws, h->w1p, h->Xt, h->tu_wimg, h->tu_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& g : h->step_graph) if (g) cudaGraphExecDestroy(g);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -384,10 +395,10 @@ extern "C" int tbnn_sweep_info(const tbnn_handle* h, int* kernel_kind, int* ctas
                                int* smem_bytes) {
   if (!h) return fail("null handle");
   const ModelPlan& p = h->use_usweep ? h->uw : (h->use_wide2 ? h->w2 : (h->use_wide ? h->wp : h->mp));
-  if (kernel_kind) *kernel_kind = h->use_usweep ? 3 : (h->use_wide2 ? 2 : (h->use_wide ? 1 : 0));
-  if (ctas_per_chain) *ctas_per_chain = h->S;
-  if (rows_per_tile) *rows_per_tile = p.TR;
-  if (smem_bytes) *smem_bytes = (int)((size_t)p.smem_elems * h->esz);
+  if (kernel_kind) *kernel_kind = h->use_tu ? 4 : (h->use_usweep ? 3 : (h->use_wide2 ? 2 : (h->use_wide ? 1 : 0)));
+  if (ctas_per_chain) *ctas_per_chain = h->use_tu ? h->S_tu : h->S;
+  if (rows_per_tile) *rows_per_tile = h->use_tu ? 128 : p.TR;
+  if (smem_bytes) *smem_bytes = h->use_tu ? h->tu.smem_bytes : (int)((size_t)p.smem_elems * h->esz);
   return 0;
 }
 
@@ -417,6 +428,8 @@ static int after_data(tbnn_handle* h, long long n_rows, cudaStream_t st = 0) {
     const int s_tile = (int)((ntile + q - 1) / q);
     h->use_usweep = h->want_usweep && plan_usweep(h->mp, n_rows, s_row, SMEM_LIMIT, h->uw, h->up);
     h->S = (h->use_wide || h->use_usweep) ? s_row : s_tile;
+    h->S_tu = (int)std::max<long long>(1, std::min<long long>(smax, (n_rows + 127) / 128));
+    if (h->use_tu) h->S = h->S_tu;   // one partial count for the sweep, the forward-only statistic sweep and finalize
   }
   const size_t need = (size_t)h->C * h->S * h->mp.Ppad * h->esz;
   if (need > h->partial_cap) {
@@ -465,7 +478,12 @@ extern "C" int tbnn_set_data_host(tbnn_handle* h, const void* X, const void* Y, 
 // the row sweep: wide-first-layer kernel when planned (fp32), else the generic tile engine
 template <typename T>
 static void sweep(tbnn_handle* h, bool backward, cudaStream_t st) {
-  if (h->use_usweep && backward) {
+  if (h->use_tu && backward) {
+    launch_train_umma(h->mp, h->tu, h->num_sms, h->C, h->S_tu, (const float*)h->theta_pad, (unsigned char*)h->tu_wimg,
+                      (float*)h->tu_scratch, (const float*)h->X, (const float*)h->Y, h->N, (float*)h->partial,
+                      h->stat_part, st);
+    h->launches++;
+  } else if (h->use_usweep && backward) {
     launch_sweep_umma(h->uw, h->up, h->C, h->S, (const float*)h->theta_pad, (const float*)h->Xt, (const float*)h->Y,
                       h->N, (float*)h->partial, h->stat_part, st);
   } else if (h->use_wide2 && backward) {

@@ -1,0 +1,728 @@
+// k_train_umma.cu -- the row sweep (log-likelihood + full parameter gradient of one leapfrog step) with every
+// hidden-layer contraction on the 5th-generation tensor cores (tcgen05.mma kind::tf32, error-compensated 3xTF32,
+// fp32 accumulators in tensor memory).  Same contract as k_partial (k_main.cu): per (chain, CTA slot) a partial
+// gradient in the padded layout plus a likelihood statistic; k_finalize adds priors and does the leapfrog update.
+//
+// Reference arithmetic replaced: tf.matmul(W, A) of layer.predict (layer.py:278) for the forward pass and the
+// two GEMMs per layer TF's autodiff adds for the backward pass (dA = dZ W, dW = dZ^T A), invoked from TFP's
+// leapfrog through network.py:370-408; activations (activationFunctions.py), likelihood residuals
+// (likelihood.py:88-94,162-167,225-236) and the last (<= 4 output) layer stay on the CUDA cores.
+//
+// Shapes: networks whose dense blocks 0..G-1 all have the same output width HW in {64, 128} and the same
+// activation, followed by one last block with <= 4 outputs (C3: 1-64-64-64-1 SquarePrelu, C4: 32-128-128-128-1 ReLU).
+//
+// One persistent CTA per SM, 6 warps, three roles over two 3-stage operand rings in shared memory:
+//   warps 0-3  row workers: thread = one training row of the 128-row tile.  They read accumulators from tensor
+//              memory (tcgen05.ld), apply bias / activation / derivatives, and WRITE MMA OPERANDS: K-major chunks of
+//              32 features for the forward (A_l) and data-gradient (dZ_l) GEMMs, and transposed (K = rows) chunks for
+//              the weight-gradient GEMMs -- chunk q of those holds the 32 rows of warp q.  hi/lo TF32 split, plain
+//              SWIZZLE_NONE core matrices whose column-group stride is padded by 16 bytes so the transposed 4-byte
+//              stores are bank-conflict free.
+//   warp 4     MMA issuer (one thread): per 32-deep chunk and 8-deep k step lo*hi + hi*lo + hi*hi.
+//   warp 5     TMA producer (one thread): streams pre-split, pre-tiled weight operands (k_train_prep) from L2 with
+//              cp.async.bulk; a 128-wide network does not fit its weights (2 layers x 2 orientations x hi/lo x 64 KB)
+//              in shared memory, so they are streamed per tile (~0.5 MB / tile, L2 resident).
+// GEMM order per tile: F_0 .. F_{G-1} | B_{G-1}, W_{G-1}, .., B_1, W_1, W_0   (F: Z_l = A_{l-1} W_l^T, B: dA_{l-1} =
+// dZ_l W_l, W: [dW_l | db_l] = dZ_l^T [A_{l-1} | 1]).  The bias gradient falls out of a constant-one operand row; with
+// HW = 64 the free upper half of the M = 128 operand carries z*dA so the slope gradients (Prelu / SquarePrelu) fall
+// out of the same column.  Weight gradients are drained per tile from tensor memory and added to this CTA's slice
+// of the partial buffer with vector reductions (red.global.add.v4.f32): the accumulation chain inside the tensor
+// core stays 48 MMAs long (its accumulator rounds toward zero, profiles/r1d_summary.md).
+// Pre-activations of blocks 0..G-2 are parked in a per-CTA global scratch (L2 resident) between forward and backward.
+#include "engine.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace tbnn {
+
+constexpr int TU_THREADS = 192;
+constexpr int TU_NS = 3;                       // ring stages
+constexpr int TU_CGA = 128 * 16 + 16;          // column-group stride (bytes) of a 128-row operand chunk
+constexpr int TU_HALFA = 8 * TU_CGA;           // bytes of its hi (or lo) half
+constexpr int TU_ASTAGE = 2 * TU_HALFA;
+
+__host__ __device__ constexpr int tu_cgs(int rows) { return 128 * (rows / 8) + 16; }
+__host__ __device__ constexpr int tu_half(int rows) { return 8 * tu_cgs(rows); }
+
+__device__ __forceinline__ void ew_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add1(float* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(p), "f"(a) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// 32 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  float a[16], b[16];
+  umma::tmem_ld16(taddr, a);
+  umma::tmem_ld16(taddr + 16, b);
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v[i] = a[i]; v[16 + i] = b[i]; }
+}
+
+// column sums over the 32 lanes of a warp: on return lane i holds sum over lanes of v[i] (31 shuffles)
+__device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------ weight operand images
+// Per chain: forward image of block l (B operand [N = HW][K = in_l], K-major) for l < G and backward image
+// (B operand [N = in_l][K = HW] = W_l^T) for 1 <= l < G, in chunks of 32 k: hi half then lo half, each 8 column
+// groups of tu_cgs(HW) bytes; 16-byte group (n, kq) at (n / 8) * 128 + kq * cgs + (n % 8) * 16.
+__global__ void k_train_prep(const __grid_constant__ ModelPlan mp, const __grid_constant__ TrainUmmaPlan tp,
+                             const float* __restrict__ theta_pad, unsigned char* __restrict__ wimg) {
+  const int c = blockIdx.y;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = tp.HW, nH = HW / 32, gper = HW * 8;      // groups per chunk
+  // image list: F_0 (nK0 chunks), F_1..F_{G-1} (nH chunks each), B_1..B_{G-1}
+  int idx = gid, l = -1, bwd = 0, nch = 0;
+  for (int i = 0; i < 2 * tp.G - 1; ++i) {
+    const int li = i < tp.G ? i : i - tp.G + 1;
+    const int n = (i == 0 ? tp.nK0 : nH) * gper;
+    if (idx < n) { l = li; bwd = i >= tp.G; nch = (i == 0 ? tp.nK0 : nH); break; }
+    idx -= n;
+  }
+  if (l < 0) return;
+  (void)nch;
+  const BlockPlan& b = mp.b[l];
+  const int chunk = idx / gper, rem = idx - chunk * gper, n = rem >> 3, kq = rem & 7, k0 = chunk * 32 + kq * 4;
+  const float* th = theta_pad + (size_t)c * mp.Ppad + b.pw;
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + i;
+    if (!bwd) v[i] = (n < b.out && k < b.in) ? th[n * b.ld_in + k] : 0.f;     // W_l[n][k]
+    else v[i] = (k < b.out && n < b.in) ? th[k * b.ld_in + n] : 0.f;          // W_l[k][n]
+  }
+  float hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) umma::split_tf32(v[i], hi[i], lo[i]);
+  const int cgs = tu_cgs(HW);
+  unsigned char* base = wimg + (size_t)c * tp.wimg_chain + (bwd ? tp.bimg[l] : tp.fimg[l]) + (size_t)chunk * 2 * tu_half(HW);
+  const int off = (n >> 3) * 128 + kq * cgs + (n & 7) * 16;
+  *reinterpret_cast<float4*>(base + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(base + tu_half(HW) + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ------------------------------------------------------------------ activation helpers (compile-time kind)
+// ACTK: ACT_RELU | ACT_SQPRELU (any slope-type activation: z is kept, `slope` is the effective negative-side
+// slope) | -1 (parameter-free activation evaluated through act_fwd / act_deriv_from_out)
+template <int ACTK> __device__ __forceinline__ float tu_keep(int act, float z, float a) {   // what the backward pass needs
+  return ACTK == ACT_SQPRELU ? z : a;
+}
+template <int ACTK> __device__ __forceinline__ float tu_act(int act, float z, float slope) {
+  if (ACTK == ACT_RELU) return fmaxf(z, 0.f);
+  if (ACTK == ACT_SQPRELU) return z < 0.f ? slope * z : z;
+  return act_fwd<float>(act, z, 0.f);
+}
+template <int ACTK> __device__ __forceinline__ float tu_from_keep(int act, float s, float slope) {   // activation output from the kept value
+  if (ACTK == ACT_SQPRELU) return s < 0.f ? slope * s : s;
+  return s;
+}
+template <int ACTK> __device__ __forceinline__ float tu_deriv(int act, float s, float slope) {
+  if (ACTK == ACT_RELU) return s > 0.f ? 1.f : 0.f;
+  if (ACTK == ACT_SQPRELU) return s < 0.f ? slope : 1.f;
+  return act_deriv_from_out<float>(act, s);
+}
+
+// this thread's row as a K-major operand chunk of 32 features: 8 column groups, hi and lo halves
+__device__ __forceinline__ void put_row_chunk(uint32_t stage, int r, const float* v) {
+#pragma unroll
+  for (int kq = 0; kq < 8; ++kq) {
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) umma::split_tf32(v[4 * kq + i], h[i], l[i]);
+    const uint32_t a = stage + kq * TU_CGA + r * 16;
+    sts128(a, h[0], h[1], h[2], h[3]);
+    sts128(a + TU_HALFA, l[0], l[1], l[2], l[3]);
+  }
+}
+// one value of the transposed (K = rows) operand: operand row n, k = lane, column-group stride cgs
+__device__ __forceinline__ void put_t(uint32_t stage, int half, int cgs, int n, int lane, float v) {
+  float h, l;
+  umma::split_tf32(v, h, l);
+  const uint32_t a = stage + (n >> 3) * 128 + (lane >> 2) * cgs + (n & 7) * 16 + (lane & 3) * 4;
+  sts32(a, h);
+  sts32(a + half, l);
+}
+
+struct TuBars {
+  uint64_t fullA[TU_NS], emptyA[TU_NS], fullB[TU_NS], emptyB[TU_NS], accfull[3];
+};
+
+template <int HW, int ACTK>
+__global__ void __launch_bounds__(TU_THREADS, 1)
+k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ TrainUmmaPlan tp, int C, int S,
+             const float* __restrict__ theta_pad, const unsigned char* __restrict__ wimg,
+             const float* __restrict__ X, const float* __restrict__ Y, long long N, float* __restrict__ partial,
+             double* __restrict__ stat_part, float* __restrict__ scratch) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ uint32_t tmem_slot;
+  constexpr int nH = HW / 32;                   // chunks of a hidden-width contraction
+  constexpr int NWH = HW + 16;                  // N of a hidden weight-gradient GEMM: [A | 1 | pad]
+  constexpr bool SLOPES = ACTK == ACT_SQPRELU;
+  constexpr bool STACKQ = SLOPES && HW == 64;   // slope gradients ride in operand rows 64..127
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = tp.G, D = mp.D, OUT = mp.OUT, hact = tp.act;
+  TuBars* bars = reinterpret_cast<TuBars*>(smraw + tp.off_bar);
+  float* par = reinterpret_cast<float*>(smraw + tp.off_par);
+  const uint32_t ringA = smem_u32(smraw + tp.off_a), ringB = smem_u32(smraw + tp.off_b);
+  const long long ntile = (N + 127) >> 7;
+  const int nitem = C * S;
+
+  if (tid == 0) {
+    for (int i = 0; i < TU_NS; ++i) {
+      mbar_init(&bars->fullA[i], 4);
+      mbar_init(&bars->emptyA[i], 1);
+      mbar_init(&bars->fullB[i], 1);
+      mbar_init(&bars->emptyB[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(&bars->accfull[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) umma::tmem_alloc(&tmem_slot, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = tmem_slot;
+  // tensor memory: accumulators of the F / B GEMMs ping-pong in columns [0,128) and [128,256); W GEMMs in [256, 256+144)
+  const uint32_t accCol[3] = {0u, 128u, 256u};
+
+  if (warp == 5) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      uint32_t cc = 0;
+      const uint32_t cbytes = 2u * tu_half(HW);
+      // The four chunks of a weight-gradient GEMM are filled by the row workers, but this thread still has to SEE
+      // each stage's release: a parity wait is only unambiguous while the waiter is at most one phase behind.
+      auto skip_w = [&]() {
+        for (int q = 0; q < 4; ++q, ++cc) {
+          const uint32_t st = cc % TU_NS, use = cc / TU_NS;
+          mbar_wait_parked(&bars->emptyB[st], (use & 1u) ^ 1u);
+        }
+      };
+      for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
+        const int c = item / S, s = item - c * S;
+        const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
+        const unsigned char* img = wimg + (size_t)c * tp.wimg_chain;
+        for (long long t = t0; t < t1; ++t) {
+          for (int l = 0; l < G; ++l) {
+            const int nch = l == 0 ? tp.nK0 : nH;
+            for (int ch = 0; ch < nch; ++ch, ++cc) {
+              const uint32_t st = cc % TU_NS, use = cc / TU_NS;
+              mbar_wait_parked(&bars->emptyB[st], (use & 1u) ^ 1u);
+              mbar_expect_tx(&bars->fullB[st], cbytes);
+              bulk_g2s(smraw + tp.off_b + st * tp.b_stage, img + tp.fimg[l] + (size_t)ch * cbytes, cbytes, &bars->fullB[st]);
+            }
+          }
+          for (int l = G - 1; l >= 1; --l) {
+            for (int ch = 0; ch < nH; ++ch, ++cc) {
+              const uint32_t st = cc % TU_NS, use = cc / TU_NS;
+              mbar_wait_parked(&bars->emptyB[st], (use & 1u) ^ 1u);
+              mbar_expect_tx(&bars->fullB[st], cbytes);
+              bulk_g2s(smraw + tp.off_b + st * tp.b_stage, img + tp.bimg[l] + (size_t)ch * cbytes, cbytes, &bars->fullB[st]);
+            }
+            skip_w();    // W_l: both operands come from the row workers
+          }
+          skip_w();      // W_0
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      uint32_t cc = 0;
+      const uint32_t idF = umma::idesc_tf32(128, HW, false, false);
+      const uint32_t idWh = umma::idesc_tf32(128, NWH, false, false);
+      const uint32_t idW0 = umma::idesc_tf32(128, tp.N0w, false, false);
+      // one GEMM: `nch` chunks of `ks` (last chunk: ks_last) k steps into accumulator `acc`
+      auto gemm = [&](int nch, int ks_full, int ks_last, uint32_t idesc, int cgsB, int acc) {
+        const uint32_t d = umma::tmem_addr(tbase, 0, accCol[acc]);
+        const uint32_t halfB = 8u * cgsB;
+        for (int ch = 0; ch < nch; ++ch, ++cc) {
+          const uint32_t st = cc % TU_NS, use = cc / TU_NS;
+          mbar_wait(&bars->fullA[st], use & 1u);
+          mbar_wait(&bars->fullB[st], use & 1u);
+          umma::fence_after_sync();
+          const uint32_t a0 = ringA + st * TU_ASTAGE, b0 = ringB + st * tp.b_stage;
+          const int ks = ch == nch - 1 ? ks_last : ks_full;
+          for (int k = 0; k < ks; ++k) {
+            const uint64_t dAh = umma::smem_desc(a0 + k * 2 * TU_CGA, TU_CGA, 128u);
+            const uint64_t dAl = umma::smem_desc(a0 + TU_HALFA + k * 2 * TU_CGA, TU_CGA, 128u);
+            const uint64_t dBh = umma::smem_desc(b0 + k * 2 * cgsB, cgsB, 128u);
+            const uint64_t dBl = umma::smem_desc(b0 + halfB + k * 2 * cgsB, cgsB, 128u);
+            umma::mma_tf32_ss(d, dAl, dBh, idesc, ch > 0 || k > 0);
+            umma::mma_tf32_ss(d, dAh, dBl, idesc, true);
+            umma::mma_tf32_ss(d, dAh, dBh, idesc, true);
+          }
+          umma::commit(&bars->emptyA[st]);
+          umma::commit(&bars->emptyB[st]);
+        }
+        umma::commit(&bars->accfull[acc]);
+      };
+      for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
+        const int c = item / S, s = item - c * S;
+        (void)c;
+        const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
+        for (long long t = t0; t < t1; ++t) {
+          int acc = 0;
+          const int ks0 = (tp.K0p - 32 * (tp.nK0 - 1)) / 8;
+          gemm(tp.nK0, 4, ks0, idF, tu_cgs(HW), acc);
+          for (int l = 1; l < G; ++l) { acc ^= 1; gemm(nH, 4, 4, idF, tu_cgs(HW), acc); }
+          for (int l = G - 1; l >= 1; --l) {
+            acc ^= 1;
+            gemm(nH, 4, 4, idF, tu_cgs(HW), acc);          // B_l: dA_{l-1}
+            gemm(4, 4, 4, idWh, tu_cgs(NWH), 2);           // W_l
+          }
+          gemm(4, 4, 4, idW0, tu_cgs(tp.N0w), 2);          // W_0
+        }
+      }
+    }
+  } else {
+    // ================================================================ row workers (thread = row)
+    const int r = tid;                                   // row of the tile = TMEM lane
+    const uint32_t lane_t = (uint32_t)(32 * warp) << 16;
+    uint32_t cc = 0, accuse[3] = {0u, 0u, 0u};
+    float* bias_s = par + tp.par_bias;                   // [G][HW]
+    float* slope_s = par + tp.par_slope;                 // [G][HW] effective negative-side slope
+    float* sfac_s = par + tp.par_sraw;                   // [G][HW] d(effective slope)/d(parameter): 2 s or 1
+    float* wl_s = par + tp.par_wl;                       // [OUT][HW], then bias [4]
+    float* accl_s = par + tp.par_accl;                   // [OUT][HW] + [4]: gradient of the last block
+    const BlockPlan& bL = mp.b[G];
+    float* scr = scratch + (size_t)blockIdx.x * tp.scratch_cta;
+
+    auto wait_acc = [&](int a) {
+      mbar_wait(&bars->accfull[a], accuse[a] & 1u);
+      accuse[a]++;
+      umma::fence_after_sync();
+    };
+    // all four warps publish one K-major chunk of ring A
+    auto publish_A = [&](uint32_t st) {
+      fence_proxy_async();
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->fullA[st]);
+    };
+
+    for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
+      const int c = item / S, s = item - c * S;
+      const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
+      const float* th = theta_pad + (size_t)c * mp.Ppad;
+      float* gout = partial + ((size_t)c * S + s) * mp.Ppad;
+      ew_barrier();                                      // previous item's parameters are dead
+      for (int e = tid; e < G * HW; e += 128) {
+        const int l = e / HW, j = e - l * HW;
+        const BlockPlan& b = mp.b[l];
+        bias_s[e] = th[b.pb + j];
+        float sl = 0.f, fac = 0.f;
+        if (b.act == ACT_PRELU) { sl = th[b.ps + j]; fac = 1.f; }
+        else if (b.act == ACT_SQPRELU) { const float t = th[b.ps + j]; sl = t * t; fac = 2.f * t; }
+        else if (b.act == ACT_LEAKY) sl = (float)b.alpha;
+        slope_s[e] = sl;
+        sfac_s[e] = fac;
+      }
+      for (int e = tid; e < OUT * HW + 4; e += 128) {
+        float v = 0.f;
+        if (e < OUT * HW) { const int o = e / HW, k = e - o * HW; v = th[bL.pw + o * bL.ld_in + k]; }
+        else if (e - OUT * HW < OUT) v = th[bL.pb + e - OUT * HW];
+        wl_s[e] = v;
+        accl_s[e] = 0.f;
+      }
+      for (int i = 4 * tid; i < mp.Ppad; i += 4 * 128) *reinterpret_cast<float4*>(gout + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      __threadfence();
+      ew_barrier();
+      double stat = 0.0;
+
+      for (long long t = t0; t < t1; ++t) {
+        const long long row = t * 128 + r;
+        const bool valid = row < N;
+        const float* xrow = X + (valid ? row : 0) * (long long)D;
+        // ------------------------------------------------ F_0 operand: this row of X
+        for (int ch = 0; ch < tp.nK0; ++ch, ++cc) {
+          const uint32_t st = cc % TU_NS, use = cc / TU_NS;
+          mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
+          const uint32_t stage = ringA + st * TU_ASTAGE;
+          const int ngr = min(8, (tp.K0p - 32 * ch) >> 2);
+          for (int kq = 0; kq < ngr; ++kq) {
+            float h[4], l4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int k = 32 * ch + 4 * kq + i;
+              const float x = (valid && k < D) ? xrow[k] : 0.f;
+              umma::split_tf32(x, h[i], l4[i]);
+            }
+            const uint32_t a = stage + kq * TU_CGA + r * 16;
+            sts128(a, h[0], h[1], h[2], h[3]);
+            sts128(a + TU_HALFA, l4[0], l4[1], l4[2], l4[3]);
+          }
+          publish_A(st);
+        }
+        // ------------------------------------------------ forward through the hidden blocks
+        int acc = 0;
+        for (int l = 0; l < G - 1; ++l, acc ^= 1) {
+          wait_acc(acc);
+          const float* bz = bias_s + l * HW;
+          const float* sl = slope_s + l * HW;
+          float* sc = scr + (size_t)l * HW * 128;
+#pragma unroll 1
+          for (int j = 0; j < nH; ++j) {
+            float v[32];
+            tmem_ld32(tbase + lane_t + accCol[acc] + 32 * j, v);
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              float keep[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int col = 32 * j + 4 * q4 + i;
+                const float z = v[4 * q4 + i] + bz[col];
+                const float a = tu_act<ACTK>(hact, z, SLOPES ? sl[col] : 0.f);
+                keep[i] = tu_keep<ACTK>(hact, z, a);
+                v[4 * q4 + i] = a;
+              }
+              *reinterpret_cast<float4*>(sc + ((size_t)(8 * j + q4) * 128 + r) * 4) = make_float4(keep[0], keep[1], keep[2], keep[3]);
+            }
+            const uint32_t st = cc % TU_NS, use = cc / TU_NS;
+            mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
+            put_row_chunk(ringA + st * TU_ASTAGE, r, v);
+            publish_A(st);
+            ++cc;
+          }
+        }
+        // ------------------------------------------------ last hidden block + last block + likelihood
+        float dz[HW];                                   // kept value of block G-1, then dZ_{G-1}
+        float qv[STACKQ ? HW : 1];
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          wait_acc(acc);
+          const float* bz = bias_s + (G - 1) * HW;
+          const float* sl = slope_s + (G - 1) * HW;
+#pragma unroll
+          for (int j = 0; j < nH; ++j) {
+            float v[32];
+            tmem_ld32(tbase + lane_t + accCol[acc] + 32 * j, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = 32 * j + i;
+              const float z = v[i] + bz[col];
+              const float a = tu_act<ACTK>(hact, z, SLOPES ? sl[col] : 0.f);
+              dz[col] = tu_keep<ACTK>(hact, z, a);
+#pragma unroll
+              for (int o = 0; o < 4; ++o)
+                if (o < OUT) f[o] = fmaf(wl_s[o * HW + col], a, f[o]);
+            }
+          }
+          acc ^= 1;
+        }
+        float dfl[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          const float lo = 1e-8f, hi = (float)(1 - 1e-7);          // likelihood.py:229-230
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            if (o < OUT) {
+              const float fo = act_fwd<float>(bL.act, f[o] + wl_s[OUT * HW + o], 0.f);
+              if (valid) {
+                const float y = Y[row * (long long)OUT + o];
+                float df;
+                if (mp.lik == LIK_BERN) {
+                  const float p = fo < lo ? lo : (fo > hi ? hi : fo);
+                  stat += (double)((1.f - y) * log1pf(-p) + y * logf(p));
+                  df = (fo < lo || fo > hi) ? 0.f : (y / p - (1.f - y) / (1.f - p));
+                } else {
+                  const float res = y - fo;
+                  stat += (double)res * (double)res;
+                  df = res;
+                }
+                dfl[o] = df * act_deriv_from_out<float>(bL.act, fo);
+              }
+            }
+          }
+        }
+        // gradient of the last block (column sums over the tile's rows), dA_{G-1}, dZ_{G-1}
+        {
+          const float* sl = slope_s + (G - 1) * HW;
+#pragma unroll
+          for (int g = 0; g < nH; ++g) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              if (o < OUT) {
+                float pr[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pr[i] = dfl[o] * tu_from_keep<ACTK>(hact, dz[32 * g + i], SLOPES ? sl[32 * g + i] : 0.f);
+                const float cs = colsum32(pr, lane);
+                atomicAdd(&accl_s[o * HW + 32 * g + lane], cs);
+              }
+            }
+          }
+          float bsum[4];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            float v = dfl[o];
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+            bsum[o] = v;
+          }
+          if (lane == 0)
+            for (int o = 0; o < OUT; ++o) atomicAdd(&accl_s[OUT * HW + o], bsum[o]);
+#pragma unroll
+          for (int k = 0; k < HW; ++k) {
+            float dA = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+              if (o < OUT) dA = fmaf(dfl[o], wl_s[o * HW + k], dA);
+            const float sk = dz[k];
+            if (STACKQ) qv[k] = sk < 0.f ? sk * dA : 0.f;
+            dz[k] = dA * tu_deriv<ACTK>(hact, sk, SLOPES ? sl[k] : 0.f);
+          }
+        }
+        // ------------------------------------------------ backward
+        for (int l = G - 1; l >= 0; --l) {
+          // (1) dZ_l as the A operand of B_l (dA_{l-1} = dZ_l W_l): critical path first
+          if (l >= 1) {
+#pragma unroll
+            for (int j = 0; j < nH; ++j, ++cc) {
+              const uint32_t st = cc % TU_NS, use = cc / TU_NS;
+              mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
+              put_row_chunk(ringA + st * TU_ASTAGE, r, &dz[32 * j]);
+              publish_A(st);
+            }
+          }
+          // (2) drain the previous weight-gradient GEMM (W_{l+1}) before its accumulator is reused
+          if (l < G - 1) {
+            const BlockPlan& bp = mp.b[l + 1];
+            wait_acc(2);
+            if (r < HW) {
+              float* gw = gout + bp.pw + r * bp.ld_in;
+#pragma unroll 1
+              for (int n0 = 0; n0 < HW; n0 += 16) {
+                float v[16];
+                umma::tmem_ld16(tbase + lane_t + accCol[2] + n0, v);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) red_add4(gw + n0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+              }
+            }
+            {
+              float v[8];
+              umma::tmem_ld8(tbase + lane_t + accCol[2] + HW, v);
+              umma::tmem_ld_wait();
+              if (r < HW) red_add1(gout + bp.pb + r, v[0]);
+              else if (STACKQ && act_has_slopes(bp.act)) red_add1(gout + bp.ps + (r - HW), v[0] * sfac_s[(l + 1) * HW + (r - HW)]);
+            }
+            umma::fence_before_sync();
+            ew_barrier();
+          }
+          // (3) operands of W_l, chunk `warp` = the 32 rows of this warp
+          {
+            const uint32_t cq = cc + warp, st = cq % TU_NS, use = cq / TU_NS;
+            mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
+            mbar_wait(&bars->emptyB[st], (use & 1u) ^ 1u);
+            const uint32_t sa = ringA + st * TU_ASTAGE, sb = ringB + st * tp.b_stage;
+#pragma unroll
+            for (int j = 0; j < HW; ++j) put_t(sa, TU_HALFA, TU_CGA, j, lane, dz[j]);
+            if (HW == 64) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) put_t(sa, TU_HALFA, TU_CGA, 64 + j, lane, STACKQ ? qv[STACKQ ? j : 0] : 0.f);
+            }
+            if (l >= 1) {
+              const int cgs = tu_cgs(NWH), half = tu_half(NWH);
+              const float* sc = scr + (size_t)(l - 1) * HW * 128;
+              const float* sl = slope_s + (l - 1) * HW;
+#pragma unroll 4
+              for (int g4 = 0; g4 < HW / 4; ++g4) {
+                const float4 kv = *reinterpret_cast<const float4*>(sc + ((size_t)g4 * 128 + r) * 4);
+                const float k4[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  put_t(sb, half, cgs, 4 * g4 + i, lane, tu_from_keep<ACTK>(hact, k4[i], SLOPES ? sl[4 * g4 + i] : 0.f));
+              }
+              put_t(sb, half, cgs, HW, lane, 1.f);
+            } else {
+              const int cgs = tu_cgs(tp.N0w), half = tu_half(tp.N0w);
+              for (int k = 0; k < D; ++k) put_t(sb, half, cgs, k, lane, valid ? xrow[k] : 0.f);
+              put_t(sb, half, cgs, D, lane, 1.f);
+            }
+            fence_proxy_async();
+            umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_n(&bars->fullA[st], 4);
+              mbar_arrive(&bars->fullB[st]);
+            }
+            cc += 4;
+          }
+          // (4) dA_{l-1} from tensor memory -> dZ_{l-1}
+          if (l >= 1) {
+            wait_acc(acc);
+            const float* sc = scr + (size_t)(l - 1) * HW * 128;
+            const float* sl = slope_s + (l - 1) * HW;
+#pragma unroll
+            for (int j = 0; j < nH; ++j) {
+              float v[32];
+              tmem_ld32(tbase + lane_t + accCol[acc] + 32 * j, v);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 kv = *reinterpret_cast<const float4*>(sc + ((size_t)(8 * j + q4) * 128 + r) * 4);
+                const float k4[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int col = 32 * j + 4 * q4 + i;
+                  const float dA = v[4 * q4 + i];
+                  if (STACKQ) qv[STACKQ ? col : 0] = k4[i] < 0.f ? k4[i] * dA : 0.f;
+                  dz[col] = dA * tu_deriv<ACTK>(hact, k4[i], SLOPES ? sl[col] : 0.f);
+                }
+              }
+            }
+            acc ^= 1;
+          }
+        }
+        // ------------------------------------------------ drain W_0
+        {
+          const BlockPlan& b0 = mp.b[0];
+          wait_acc(2);
+          if (r < HW) {
+            float* gw = gout + b0.pw + r * b0.ld_in;
+            for (int n0 = 0; n0 < tp.N0w; n0 += 8) {
+              float v[8];
+              umma::tmem_ld8(tbase + lane_t + accCol[2] + n0, v);
+              umma::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int n = n0 + i;
+                if (n < D) red_add1(gw + n, v[i]);
+                else if (n == D) red_add1(gout + b0.pb + r, v[i]);
+              }
+            }
+          } else if (STACKQ && act_has_slopes(b0.act)) {
+            float v[8];
+            umma::tmem_ld8(tbase + lane_t + accCol[2] + (D & ~7), v);
+            umma::tmem_ld_wait();
+            float pick = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i == (D & 7)) pick = v[i];
+            red_add1(gout + b0.ps + (r - HW), pick * sfac_s[r - HW]);
+          }
+          umma::fence_before_sync();
+          ew_barrier();
+        }
+      }
+      // ---------------------------------------------------- item epilogue: last block gradient, statistic
+      ew_barrier();
+      for (int e = tid; e < OUT * HW; e += 128) {
+        const int o = e / HW, k = e - o * HW;
+        gout[bL.pw + o * bL.ld_in + k] = accl_s[e];
+      }
+      if (tid < OUT) gout[bL.pb + tid] = accl_s[OUT * HW + tid];
+      {
+        double* red = reinterpret_cast<double*>(par + tp.par_accl + OUT * HW + 4);
+        const double w = warp_sum(stat);
+        if (lane == 0) red[warp] = w;
+        ew_barrier();
+        if (tid == 0) stat_part[(size_t)c * S + s] = red[0] + red[1] + red[2] + red[3];
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 4) umma::tmem_dealloc(tbase, 512);
+}
+
+// ------------------------------------------------------------------ host side
+static inline int tu_pad(int x, int m) { return (x + m - 1) / m * m; }
+
+bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) {
+  const int G = mp.nb - 1;
+  if (G < 2 || G > MAXB - 1) return false;
+  const int HW = mp.b[0].out;
+  if (HW != 64 && HW != 128) return false;
+  if (mp.OUT > 4 || mp.D > 128 || mp.D < 1) return false;
+  const int act = mp.b[0].act;
+  for (int l = 0; l < G; ++l) {
+    if (mp.b[l].out != HW || mp.b[l].act != act) return false;
+    if (l >= 1 && mp.b[l].in != HW) return false;
+  }
+  if (act_has_slopes(act) && HW != 64) return false;      // slope gradients ride in the free upper operand half
+  const BlockPlan& bL = mp.b[G];
+  if (bL.in != HW || act_keeps_z(bL.act)) return false;
+  tp.G = G; tp.HW = HW; tp.act = act;
+  tp.K0p = tu_pad(mp.D, 8);
+  tp.nK0 = (tp.K0p + 31) / 32;
+  tp.N0w = tu_pad(mp.D + 1, 16);
+  const int chunk = 2 * tu_half(HW);
+  int cur = 0;
+  for (int l = 0; l < G; ++l) { tp.fimg[l] = cur; cur += (l == 0 ? tp.nK0 : HW / 32) * chunk; }
+  tp.bimg[0] = 0;
+  for (int l = 1; l < G; ++l) { tp.bimg[l] = cur; cur += (HW / 32) * chunk; }
+  tp.wimg_chain = cur;
+  tp.a_stage = TU_ASTAGE;
+  tp.b_stage = std::max(chunk, std::max(2 * tu_half(HW + 16), 2 * tu_half(tp.N0w)));
+  tp.b_stage = tu_pad(tp.b_stage, 128);
+  int off = 0;
+  tp.off_a = off; off += TU_NS * tp.a_stage;
+  off = tu_pad(off, 128);
+  tp.off_b = off; off += TU_NS * tp.b_stage;
+  tp.off_par = off;
+  int pf = 0;
+  tp.par_bias = pf; pf += G * HW;
+  tp.par_slope = pf; pf += G * HW;
+  tp.par_sraw = pf; pf += G * HW;
+  tp.par_wl = pf; pf += mp.OUT * HW + 4;
+  tp.par_accl = pf; pf += mp.OUT * HW + 4 + 16;          // + 8 doubles of reduction scratch
+  off += pf * 4;
+  off = tu_pad(off, 16);
+  tp.off_bar = off; off += (int)sizeof(TuBars);
+  tp.smem_bytes = off;
+  tp.scratch_cta = (G - 1) * HW * 128;
+  return (size_t)off <= smem_limit;
+}
+
+size_t train_umma_wimg_bytes(const TrainUmmaPlan& tp, int C) { return (size_t)C * tp.wimg_chain; }
+size_t train_umma_scratch_bytes(const TrainUmmaPlan& tp, int num_sms) { return (size_t)num_sms * tp.scratch_cta * 4; }
+
+void launch_train_umma(const ModelPlan& mp, const TrainUmmaPlan& tp, int num_sms, int C, int S, const float* theta_pad,
+                       unsigned char* wimg, float* scratch, const float* X, const float* Y, long long N,
+                       float* partial, double* stat_part, cudaStream_t st) {
+  const int HW = tp.HW;
+  const int groups = (tp.nK0 + (2 * tp.G - 2) * (HW / 32)) * HW * 8;
+  k_train_prep<<<dim3((groups + 255) / 256, C), 256, 0, st>>>(mp, tp, theta_pad, wimg);
+  const int grid = std::min(num_sms, C * S);
+  const int actk = tp.act == ACT_RELU ? ACT_RELU : (act_keeps_z(tp.act) ? ACT_SQPRELU : -1);
+#define TU_LAUNCH(HWV, AK)                                                                                       \
+  do {                                                                                                           \
+    cudaFuncSetAttribute(k_train_umma<HWV, AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);     \
+    k_train_umma<HWV, AK><<<grid, TU_THREADS, tp.smem_bytes, st>>>(mp, tp, C, S, theta_pad, wimg, X, Y, N,       \
+                                                                   partial, stat_part, scratch);                 \
+  } while (0)
+  if (HW == 64) {
+    if (actk == ACT_RELU) TU_LAUNCH(64, ACT_RELU);
+    else if (actk == ACT_SQPRELU) TU_LAUNCH(64, ACT_SQPRELU);
+    else TU_LAUNCH(64, -1);
+  } else {
+    if (actk == ACT_RELU) TU_LAUNCH(128, ACT_RELU);
+    else if (actk == ACT_SQPRELU) TU_LAUNCH(128, ACT_SQPRELU);
+    else TU_LAUNCH(128, -1);
+  }
+#undef TU_LAUNCH
+}
+
+}  // namespace tbnn

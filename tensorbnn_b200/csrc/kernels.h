@@ -107,6 +107,29 @@ void launch_sweep_umma(const ModelPlan& wp, const USweepPlan& up, int C, int S, 
                        const float* Xt, const float* Y, long long N, float* partial, double* stat_part,
                        cudaStream_t st);
 
+// tcgen05 (3xTF32) training row sweep for networks whose hidden blocks are GEMM-shaped (k_train_umma.cu), fp32,
+// forward + backward; same partial / stat_part contract as Launch<float>::partial.
+struct TrainUmmaPlan {
+  int G;                        // GEMM blocks 0..G-1 (the hidden blocks); block G = last block, on the CUDA cores
+  int HW;                       // hidden width: out of blocks 0..G-1 and in of blocks 1..G (64 or 128)
+  int K0p, nK0;                 // padded input width (multiple of 8) and its 32-deep chunks
+  int N0w;                      // N of the block-0 weight-gradient GEMM: pad16(D + 1)
+  int act;                      // activation shared by the hidden blocks
+  int wimg_chain;               // bytes of one chain's weight operand images
+  int fimg[MAXB], bimg[MAXB];   // byte offsets of the forward / backward operand image of block l
+  int a_stage, b_stage;         // bytes of one ring stage
+  int off_a, off_b, off_par, off_bar;                          // shared-memory byte offsets
+  int par_bias, par_slope, par_sraw, par_wl, par_accl;         // float offsets inside the parameter region
+  int smem_bytes;
+  int scratch_cta;              // floats of pre-activation scratch per CTA
+};
+bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit);
+size_t train_umma_wimg_bytes(const TrainUmmaPlan& tp, int C);
+size_t train_umma_scratch_bytes(const TrainUmmaPlan& tp, int num_sms);
+void launch_train_umma(const ModelPlan& mp, const TrainUmmaPlan& tp, int num_sms, int C, int S, const float* theta_pad,
+                       unsigned char* wimg, float* scratch, const float* X, const float* Y, long long N,
+                       float* partial, double* stat_part, cudaStream_t st);
+
 // tcgen05 (3xTF32) posterior-predictive sweep (k_predict_umma.cu), fp32 only; samples are FLAT [S][P].
 bool predict_umma_supported(const ModelPlan& mp);
 bool launch_predict_umma(const ModelPlan& mp, int num_sms, const float* samples, long long s0, long long S_chunk,

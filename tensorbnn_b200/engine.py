@@ -65,7 +65,7 @@ class Engine(object):
         """dict(kernel=..., ctas_per_chain=..., rows_per_tile=..., smem_bytes=...) of the planned row sweep."""
         k, s, r, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _lib.check(self.lib.tbnn_sweep_info(self.h, C.byref(k), C.byref(s), C.byref(r), C.byref(b)))
-        return {"kernel": ["k_partial", "k_sweep_wide", "k_sweep_wide2", "k_sweep_umma"][k.value], "ctas_per_chain": s.value,
+        return {"kernel": ["k_partial", "k_sweep_wide", "k_sweep_wide2", "k_sweep_umma", "k_train_umma"][k.value], "ctas_per_chain": s.value,
                 "rows_per_tile": r.value, "smem_bytes": b.value}
 
     def predict_kernel(self):
