@@ -307,7 +307,8 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
     float* slope_s = par + tp.par_slope;                 // [G][HW] effective negative-side slope
     float* sfac_s = par + tp.par_sraw;                   // [G][HW] d(effective slope)/d(parameter): 2 s or 1
     float* wl_s = par + tp.par_wl;                       // [OUT][HW], then bias [4]
-    float* accl_s = par + tp.par_accl;                   // [OUT][HW] + [4]: gradient of the last block
+    float* accl_s = par + tp.par_accl + warp * (OUT * HW + 4);   // per warp [OUT][HW] + [4]: gradient of the last block
+                                                         // (summed in warp order at the end: reruns are bit-identical)
     const BlockPlan& bL = mp.b[G];
     float* scr = scratch + (size_t)blockIdx.x * tp.scratch_cta;
 
@@ -346,7 +347,8 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         if (e < OUT * HW) { const int o = e / HW, k = e - o * HW; v = th[bL.pw + o * bL.ld_in + k]; }
         else if (e - OUT * HW < OUT) v = th[bL.pb + e - OUT * HW];
         wl_s[e] = v;
-        accl_s[e] = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) par[tp.par_accl + w * (OUT * HW + 4) + e] = 0.f;
       }
       for (int i = 4 * tid; i < mp.Ppad; i += 4 * 128) *reinterpret_cast<float4*>(gout + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       __threadfence();
@@ -469,7 +471,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
 #pragma unroll
                 for (int i = 0; i < 32; ++i) pr[i] = dfl[o] * tu_from_keep<ACTK>(hact, dz[32 * g + i], SLOPES ? sl[32 * g + i] : 0.f);
                 const float cs = colsum32(pr, lane);
-                atomicAdd(&accl_s[o * HW + 32 * g + lane], cs);
+                accl_s[o * HW + 32 * g + lane] += cs;
               }
             }
           }
@@ -482,7 +484,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
             bsum[o] = v;
           }
           if (lane == 0)
-            for (int o = 0; o < OUT; ++o) atomicAdd(&accl_s[OUT * HW + o], bsum[o]);
+            for (int o = 0; o < OUT; ++o) accl_s[OUT * HW + o] += bsum[o];
 #pragma unroll
           for (int k = 0; k < HW; ++k) {
             float dA = 0.f;
@@ -628,13 +630,20 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       }
       // ---------------------------------------------------- item epilogue: last block gradient, statistic
       ew_barrier();
-      for (int e = tid; e < OUT * HW; e += 128) {
-        const int o = e / HW, k = e - o * HW;
-        gout[bL.pw + o * bL.ld_in + k] = accl_s[e];
-      }
-      if (tid < OUT) gout[bL.pb + tid] = accl_s[OUT * HW + tid];
       {
-        double* red = reinterpret_cast<double*>(par + tp.par_accl + OUT * HW + 4);
+        const float* a0 = par + tp.par_accl;
+        const int ws = OUT * HW + 4;
+        for (int e = tid; e < OUT * HW; e += 128) {
+          const int o = e / HW, k = e - o * HW;
+          gout[bL.pw + o * bL.ld_in + k] = ((a0[e] + a0[ws + e]) + a0[2 * ws + e]) + a0[3 * ws + e];
+        }
+        if (tid < OUT) {
+          const int e = OUT * HW + tid;
+          gout[bL.pb + tid] = ((a0[e] + a0[ws + e]) + a0[2 * ws + e]) + a0[3 * ws + e];
+        }
+      }
+      {
+        double* red = reinterpret_cast<double*>(par + tp.par_accl + 4 * (OUT * HW + 4));
         const double w = warp_sum(stat);
         if (lane == 0) red[warp] = w;
         ew_barrier();
@@ -687,7 +696,7 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   tp.par_slope = pf; pf += G * HW;
   tp.par_sraw = pf; pf += G * HW;
   tp.par_wl = pf; pf += mp.OUT * HW + 4;
-  tp.par_accl = pf; pf += mp.OUT * HW + 4 + 16;          // + 8 doubles of reduction scratch
+  tp.par_accl = pf; pf += 4 * (mp.OUT * HW + 4) + 16;    // one per row-worker warp, + 8 doubles of reduction scratch
   off += pf * 4;
   off = tu_pad(off, 16);
   tp.off_bar = off; off += (int)sizeof(TuBars);
