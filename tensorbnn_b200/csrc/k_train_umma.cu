@@ -35,7 +35,8 @@
 
 namespace tbnn {
 
-constexpr int TU_THREADS = 192;
+constexpr int TU_THREADS = 320;          // warps 0-7 row workers, warp 8 MMA issuer (+ TMEM alloc), warp 9 TMA producer
+constexpr int TU_MMA_WARP = 8, TU_TMA_WARP = 9;
 constexpr int TU_NS = 3;                       // ring stages
 constexpr int TU_CGA = 128 * 16 + 16;          // column-group stride (bytes) of a 128-row operand chunk
 constexpr int TU_HALFA = 8 * TU_CGA;           // bytes of its hi (or lo) half
@@ -44,7 +45,7 @@ constexpr int TU_ASTAGE = 2 * TU_HALFA;
 __host__ __device__ constexpr int tu_cgs(int rows) { return 128 * (rows / 8) + 16; }
 __host__ __device__ constexpr int tu_half(int rows) { return 8 * tu_cgs(rows); }
 
-__device__ __forceinline__ void ew_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__device__ __forceinline__ void ew_barrier() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
@@ -167,7 +168,7 @@ __device__ __forceinline__ void put_t(uint32_t stage, int half, int cgs, int n, 
 }
 
 struct TuBars {
-  uint64_t fullA[TU_NS], emptyA[TU_NS], fullB[TU_NS], emptyB[TU_NS], accfull[3];
+  uint64_t fullA[TU_NS], emptyA[TU_NS], fullB[TU_NS], emptyB[TU_NS], accfull[2], accfree[2];
 };
 
 template <int HW, int ACTK>
@@ -179,6 +180,8 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ uint32_t tmem_slot;
   constexpr int nH = HW / 32;                   // chunks of a hidden-width contraction
+  constexpr int HH = HW / 2;                    // columns per row worker (two threads share a row)
+  constexpr int nHH = HH / 32;                  // chunks per column group
   constexpr int NWH = HW + 16;                  // N of a hidden weight-gradient GEMM: [A | 1 | pad]
   constexpr bool SLOPES = ACTK == ACT_SQPRELU;
   constexpr bool STACKQ = SLOPES && HW == 64;   // slope gradients ride in operand rows 64..127
@@ -192,23 +195,27 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
 
   if (tid == 0) {
     for (int i = 0; i < TU_NS; ++i) {
-      mbar_init(&bars->fullA[i], 4);
+      mbar_init(&bars->fullA[i], 8);
       mbar_init(&bars->emptyA[i], 1);
-      mbar_init(&bars->fullB[i], 1);
+      mbar_init(&bars->fullB[i], 2);
       mbar_init(&bars->emptyB[i], 1);
     }
-    for (int i = 0; i < 3; ++i) mbar_init(&bars->accfull[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->accfull[i], 1);
+      mbar_init(&bars->accfree[i], 8);
+    }
     mbar_fence_init();
   }
-  if (warp == 4) umma::tmem_alloc(&tmem_slot, 512);
+  if (warp == TU_MMA_WARP) umma::tmem_alloc(&tmem_slot, 512);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tbase = tmem_slot;
-  // tensor memory: accumulators of the F / B GEMMs ping-pong in columns [0,128) and [128,256); W GEMMs in [256, 256+144)
-  const uint32_t accCol[3] = {0u, 128u, 256u};
+  // tensor memory columns: F / B accumulator [0,128) (F GEMMs: the hi*hi products), the small products of the F GEMMs
+  // [128,256) -- two short chains instead of one long one, the accumulator rounds toward zero -- and W GEMMs [256,400)
+  constexpr uint32_t COL_BIG = 0u, COL_SMALL = 128u, COL_W = 256u;
 
-  if (warp == 5) {
+  if (warp == TU_TMA_WARP) {
     // ================================================================ TMA producer
     if (lane == 0) {
       uint32_t cc = 0;
@@ -221,6 +228,14 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           mbar_wait_parked(&bars->emptyB[st], (use & 1u) ^ 1u);
         }
       };
+      auto load = [&](const unsigned char* src) {
+        const uint32_t st = cc % TU_NS, use = cc / TU_NS;
+        mbar_wait_parked(&bars->emptyB[st], (use & 1u) ^ 1u);
+        mbar_expect_tx(&bars->fullB[st], cbytes);
+        mbar_arrive(&bars->fullB[st]);
+        bulk_g2s(smraw + tp.off_b + st * tp.b_stage, src, cbytes, &bars->fullB[st]);
+        ++cc;
+      };
       for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
         const int c = item / S, s = item - c * S;
         const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
@@ -228,36 +243,31 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         for (long long t = t0; t < t1; ++t) {
           for (int l = 0; l < G; ++l) {
             const int nch = l == 0 ? tp.nK0 : nH;
-            for (int ch = 0; ch < nch; ++ch, ++cc) {
-              const uint32_t st = cc % TU_NS, use = cc / TU_NS;
-              mbar_wait_parked(&bars->emptyB[st], (use & 1u) ^ 1u);
-              mbar_expect_tx(&bars->fullB[st], cbytes);
-              bulk_g2s(smraw + tp.off_b + st * tp.b_stage, img + tp.fimg[l] + (size_t)ch * cbytes, cbytes, &bars->fullB[st]);
-            }
+            for (int ch = 0; ch < nch; ++ch) load(img + tp.fimg[l] + (size_t)ch * cbytes);
           }
           for (int l = G - 1; l >= 1; --l) {
-            for (int ch = 0; ch < nH; ++ch, ++cc) {
-              const uint32_t st = cc % TU_NS, use = cc / TU_NS;
-              mbar_wait_parked(&bars->emptyB[st], (use & 1u) ^ 1u);
-              mbar_expect_tx(&bars->fullB[st], cbytes);
-              bulk_g2s(smraw + tp.off_b + st * tp.b_stage, img + tp.bimg[l] + (size_t)ch * cbytes, cbytes, &bars->fullB[st]);
-            }
+            for (int ch = 0; ch < nH; ++ch) load(img + tp.bimg[l] + (size_t)ch * cbytes);
             skip_w();    // W_l: both operands come from the row workers
           }
           skip_w();      // W_0
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == TU_MMA_WARP) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      uint32_t cc = 0;
+      uint32_t cc = 0, accuse[2] = {0u, 0u};
       const uint32_t idF = umma::idesc_tf32(128, HW, false, false);
       const uint32_t idWh = umma::idesc_tf32(128, NWH, false, false);
       const uint32_t idW0 = umma::idesc_tf32(128, tp.N0w, false, false);
-      // one GEMM: `nch` chunks of `ks` (last chunk: ks_last) k steps into accumulator `acc`
-      auto gemm = [&](int nch, int ks_full, int ks_last, uint32_t idesc, int cgsB, int acc) {
-        const uint32_t d = umma::tmem_addr(tbase, 0, accCol[acc]);
+      // one GEMM of `nch` chunks with `ks` (last chunk: ks_last) k steps into accumulator region `acc` (0: F / B, 1: W);
+      // split: the lo*hi and hi*lo products go to their own accumulator (forward GEMMs)
+      auto gemm = [&](int nch, int ks_last, uint32_t idesc, int cgsB, int acc, bool split) {
+        mbar_wait(&bars->accfree[acc], (accuse[acc] & 1u) ^ 1u);
+        accuse[acc]++;
+        umma::fence_after_sync();
+        const uint32_t dbig = umma::tmem_addr(tbase, 0, acc == 0 ? COL_BIG : COL_W);
+        const uint32_t dsml = split ? umma::tmem_addr(tbase, 0, COL_SMALL) : dbig;
         const uint32_t halfB = 8u * cgsB;
         for (int ch = 0; ch < nch; ++ch, ++cc) {
           const uint32_t st = cc % TU_NS, use = cc / TU_NS;
@@ -265,15 +275,16 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           mbar_wait(&bars->fullB[st], use & 1u);
           umma::fence_after_sync();
           const uint32_t a0 = ringA + st * TU_ASTAGE, b0 = ringB + st * tp.b_stage;
-          const int ks = ch == nch - 1 ? ks_last : ks_full;
+          const int ks = ch == nch - 1 ? ks_last : 4;
           for (int k = 0; k < ks; ++k) {
             const uint64_t dAh = umma::smem_desc(a0 + k * 2 * TU_CGA, TU_CGA, 128u);
             const uint64_t dAl = umma::smem_desc(a0 + TU_HALFA + k * 2 * TU_CGA, TU_CGA, 128u);
             const uint64_t dBh = umma::smem_desc(b0 + k * 2 * cgsB, cgsB, 128u);
             const uint64_t dBl = umma::smem_desc(b0 + halfB + k * 2 * cgsB, cgsB, 128u);
-            umma::mma_tf32_ss(d, dAl, dBh, idesc, ch > 0 || k > 0);
-            umma::mma_tf32_ss(d, dAh, dBl, idesc, true);
-            umma::mma_tf32_ss(d, dAh, dBh, idesc, true);
+            const bool first = ch == 0 && k == 0;
+            umma::mma_tf32_ss(dsml, dAl, dBh, idesc, !first);
+            umma::mma_tf32_ss(dsml, dAh, dBl, idesc, true);
+            umma::mma_tf32_ss(dbig, dAh, dBh, idesc, split ? !first : true);
           }
           umma::commit(&bars->emptyA[st]);
           umma::commit(&bars->emptyB[st]);
@@ -281,34 +292,35 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         umma::commit(&bars->accfull[acc]);
       };
       for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
-        const int c = item / S, s = item - c * S;
-        (void)c;
+        const int s = item % S;
         const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
         for (long long t = t0; t < t1; ++t) {
-          int acc = 0;
           const int ks0 = (tp.K0p - 32 * (tp.nK0 - 1)) / 8;
-          gemm(tp.nK0, 4, ks0, idF, tu_cgs(HW), acc);
-          for (int l = 1; l < G; ++l) { acc ^= 1; gemm(nH, 4, 4, idF, tu_cgs(HW), acc); }
+          gemm(tp.nK0, ks0, idF, tu_cgs(HW), 0, true);
+          for (int l = 1; l < G; ++l) gemm(nH, 4, idF, tu_cgs(HW), 0, true);
           for (int l = G - 1; l >= 1; --l) {
-            acc ^= 1;
-            gemm(nH, 4, 4, idF, tu_cgs(HW), acc);          // B_l: dA_{l-1}
-            gemm(4, 4, 4, idWh, tu_cgs(NWH), 2);           // W_l
+            gemm(nH, 4, idF, tu_cgs(HW), 0, false);         // B_l: dA_{l-1}
+            gemm(4, 4, idWh, tu_cgs(NWH), 1, false);        // W_l
           }
-          gemm(4, 4, 4, idW0, tu_cgs(tp.N0w), 2);          // W_0
+          gemm(4, 4, idW0, tu_cgs(tp.N0w), 1, false);       // W_0
         }
       }
     }
   } else {
-    // ================================================================ row workers (thread = row)
-    const int r = tid;                                   // row of the tile = TMEM lane
-    const uint32_t lane_t = (uint32_t)(32 * warp) << 16;
-    uint32_t cc = 0, accuse[3] = {0u, 0u, 0u};
+    // ================================================================ row workers: two threads per row, each
+    // owning HH = HW / 2 of the columns (warps 0-3: columns [0, HH), warps 4-7: [HH, HW))
+    const int grp = warp >> 2, wq = warp & 3;
+    const int r = 32 * wq + lane;                        // row of the tile = TMEM lane
+    const int cb = grp * HH;                             // first column of this thread
+    const uint32_t lane_t = (uint32_t)(32 * wq) << 16;
+    uint32_t cc = 0, accuse[2] = {0u, 0u};
     float* bias_s = par + tp.par_bias;                   // [G][HW]
     float* slope_s = par + tp.par_slope;                 // [G][HW] effective negative-side slope
     float* sfac_s = par + tp.par_sraw;                   // [G][HW] d(effective slope)/d(parameter): 2 s or 1
     float* wl_s = par + tp.par_wl;                       // [OUT][HW], then bias [4]
-    float* accl_s = par + tp.par_accl + warp * (OUT * HW + 4);   // per warp [OUT][HW] + [4]: gradient of the last block
-                                                         // (summed in warp order at the end: reruns are bit-identical)
+    float* accl_s = par + tp.par_accl + wq * (OUT * HW + 4);   // per warp quarter [OUT][HW] + [4]: gradient of the last
+                                                         // block (summed in fixed order at the end: reruns are bit-identical)
+    float* fx_s = par + tp.par_fx;                       // [2][128][4]: partial outputs of the two column groups
     const BlockPlan& bL = mp.b[G];
     float* scr = scratch + (size_t)blockIdx.x * tp.scratch_cta;
 
@@ -317,10 +329,22 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       accuse[a]++;
       umma::fence_after_sync();
     };
-    // all four warps publish one K-major chunk of ring A
-    auto publish_A = [&](uint32_t st) {
-      fence_proxy_async();
+    auto free_acc = [&](int a) {                          // this warp has read its share of accumulator region a
       umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->accfree[a]);
+    };
+    // Ring A protocol: EVERY row-worker warp takes part in EVERY chunk, in order -- slot() waits for the slot's release,
+    // the owner(s) write, done() arrives (8 arrivals complete a chunk).  A warp that skipped the chunks it does not
+    // fill would fall two phases behind (or ahead of) a barrier, where a parity wait is ambiguous.  The release of a
+    // ring-B slot is the same event (the MMA issuer commits both), so ring B needs no wait of its own here.
+    auto slot = [&](uint32_t cq) -> uint32_t {
+      const uint32_t st = cq % TU_NS, use = cq / TU_NS;
+      mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
+      return st;
+    };
+    auto done = [&](uint32_t st) {
+      fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->fullA[st]);
     };
@@ -331,7 +355,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       const float* th = theta_pad + (size_t)c * mp.Ppad;
       float* gout = partial + ((size_t)c * S + s) * mp.Ppad;
       ew_barrier();                                      // previous item's parameters are dead
-      for (int e = tid; e < G * HW; e += 128) {
+      for (int e = tid; e < G * HW; e += 256) {
         const int l = e / HW, j = e - l * HW;
         const BlockPlan& b = mp.b[l];
         bias_s[e] = th[b.pb + j];
@@ -342,7 +366,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         slope_s[e] = sl;
         sfac_s[e] = fac;
       }
-      for (int e = tid; e < OUT * HW + 4; e += 128) {
+      for (int e = tid; e < OUT * HW + 4; e += 256) {
         float v = 0.f;
         if (e < OUT * HW) { const int o = e / HW, k = e - o * HW; v = th[bL.pw + o * bL.ld_in + k]; }
         else if (e - OUT * HW < OUT) v = th[bL.pb + e - OUT * HW];
@@ -350,7 +374,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
 #pragma unroll
         for (int w = 0; w < 4; ++w) par[tp.par_accl + w * (OUT * HW + 4) + e] = 0.f;
       }
-      for (int i = 4 * tid; i < mp.Ppad; i += 4 * 128) *reinterpret_cast<float4*>(gout + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 4 * tid; i < mp.Ppad; i += 4 * 256) *reinterpret_cast<float4*>(gout + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       __threadfence();
       ew_barrier();
       double stat = 0.0;
@@ -359,141 +383,145 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         const long long row = t * 128 + r;
         const bool valid = row < N;
         const float* xrow = X + (valid ? row : 0) * (long long)D;
-        // ------------------------------------------------ F_0 operand: this row of X
-        for (int ch = 0; ch < tp.nK0; ++ch, ++cc) {
-          const uint32_t st = cc % TU_NS, use = cc / TU_NS;
-          mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
-          const uint32_t stage = ringA + st * TU_ASTAGE;
-          const int ngr = min(8, (tp.K0p - 32 * ch) >> 2);
-          for (int kq = 0; kq < ngr; ++kq) {
-            float h[4], l4[4];
+        // ------------------------------------------------ F_0 operand: this row of X (column group 0)
+        for (int ch = 0; ch < tp.nK0; ++ch) {
+          const uint32_t st = slot(cc + ch);
+          if (grp == 0) {
+            const uint32_t stage = ringA + st * TU_ASTAGE;
+            const int ngr = min(8, (tp.K0p - 32 * ch) >> 2);
+            for (int kq = 0; kq < ngr; ++kq) {
+              float h[4], l4[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int k = 32 * ch + 4 * kq + i;
-              const float x = (valid && k < D) ? xrow[k] : 0.f;
-              umma::split_tf32(x, h[i], l4[i]);
+              for (int i = 0; i < 4; ++i) {
+                const int k = 32 * ch + 4 * kq + i;
+                const float x = (valid && k < D) ? xrow[k] : 0.f;
+                umma::split_tf32(x, h[i], l4[i]);
+              }
+              const uint32_t a = stage + kq * TU_CGA + r * 16;
+              sts128(a, h[0], h[1], h[2], h[3]);
+              sts128(a + TU_HALFA, l4[0], l4[1], l4[2], l4[3]);
             }
-            const uint32_t a = stage + kq * TU_CGA + r * 16;
-            sts128(a, h[0], h[1], h[2], h[3]);
-            sts128(a + TU_HALFA, l4[0], l4[1], l4[2], l4[3]);
           }
-          publish_A(st);
+          done(st);
         }
+        cc += tp.nK0;
         // ------------------------------------------------ forward through the hidden blocks
-        int acc = 0;
-        for (int l = 0; l < G - 1; ++l, acc ^= 1) {
-          wait_acc(acc);
-          const float* bz = bias_s + l * HW;
-          const float* sl = slope_s + l * HW;
-          float* sc = scr + (size_t)l * HW * 128;
-#pragma unroll 1
-          for (int j = 0; j < nH; ++j) {
-            float v[32];
-            tmem_ld32(tbase + lane_t + accCol[acc] + 32 * j, v);
+        float dz[HH];                                   // values of this thread's columns (z / kept value / dZ)
+        float qv[STACKQ ? HH : 1];
+        for (int l = 0; l < G; ++l) {
+          wait_acc(0);
 #pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
+          for (int j = 0; j < nHH; ++j) {
+            float vb[32], vs[32];
+            tmem_ld32(tbase + lane_t + COL_BIG + cb + 32 * j, vb);
+            tmem_ld32(tbase + lane_t + COL_SMALL + cb + 32 * j, vs);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dz[32 * j + i] = vb[i] + vs[i];
+          }
+          free_acc(0);
+          const float* bz = bias_s + l * HW + cb;
+          const float* sl = slope_s + l * HW + cb;
+          if (l < G - 1) {
+            float* sc = scr + (size_t)l * HW * 128;
+#pragma unroll
+            for (int q4 = 0; q4 < HH / 4; ++q4) {
               float keep[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const int col = 32 * j + 4 * q4 + i;
-                const float z = v[4 * q4 + i] + bz[col];
+                const int col = 4 * q4 + i;
+                const float z = dz[col] + bz[col];
                 const float a = tu_act<ACTK>(hact, z, SLOPES ? sl[col] : 0.f);
                 keep[i] = tu_keep<ACTK>(hact, z, a);
-                v[4 * q4 + i] = a;
+                dz[col] = a;
               }
-              *reinterpret_cast<float4*>(sc + ((size_t)(8 * j + q4) * 128 + r) * 4) = make_float4(keep[0], keep[1], keep[2], keep[3]);
+              *reinterpret_cast<float4*>(sc + ((size_t)(cb / 4 + q4) * 128 + r) * 4) = make_float4(keep[0], keep[1], keep[2], keep[3]);
             }
-            const uint32_t st = cc % TU_NS, use = cc / TU_NS;
-            mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
-            put_row_chunk(ringA + st * TU_ASTAGE, r, v);
-            publish_A(st);
-            ++cc;
-          }
-        }
-        // ------------------------------------------------ last hidden block + last block + likelihood
-        float dz[HW];                                   // kept value of block G-1, then dZ_{G-1}
-        float qv[STACKQ ? HW : 1];
-        float f[4] = {0.f, 0.f, 0.f, 0.f};
-        {
-          wait_acc(acc);
-          const float* bz = bias_s + (G - 1) * HW;
-          const float* sl = slope_s + (G - 1) * HW;
 #pragma unroll
-          for (int j = 0; j < nH; ++j) {
-            float v[32];
-            tmem_ld32(tbase + lane_t + accCol[acc] + 32 * j, v);
+            for (int jj = 0; jj < nH; ++jj) {
+              const uint32_t st = slot(cc + jj);
+              if (jj / nHH == grp) put_row_chunk(ringA + st * TU_ASTAGE, r, &dz[32 * (jj % nHH)]);
+              done(st);
+            }
+            cc += nH;
+          } else {
+            // ---------------------------------------------- last hidden block, last block, likelihood
+            float f[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int col = 32 * j + i;
-              const float z = v[i] + bz[col];
+            for (int col = 0; col < HH; ++col) {
+              const float z = dz[col] + bz[col];
               const float a = tu_act<ACTK>(hact, z, SLOPES ? sl[col] : 0.f);
               dz[col] = tu_keep<ACTK>(hact, z, a);
 #pragma unroll
               for (int o = 0; o < 4; ++o)
-                if (o < OUT) f[o] = fmaf(wl_s[o * HW + col], a, f[o]);
+                if (o < OUT) f[o] = fmaf(wl_s[o * HW + cb + col], a, f[o]);
             }
-          }
-          acc ^= 1;
-        }
-        float dfl[4] = {0.f, 0.f, 0.f, 0.f};
-        {
-          const float lo = 1e-8f, hi = (float)(1 - 1e-7);          // likelihood.py:229-230
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            if (o < OUT) {
-              const float fo = act_fwd<float>(bL.act, f[o] + wl_s[OUT * HW + o], 0.f);
-              if (valid) {
-                const float y = Y[row * (long long)OUT + o];
-                float df;
-                if (mp.lik == LIK_BERN) {
-                  const float p = fo < lo ? lo : (fo > hi ? hi : fo);
-                  stat += (double)((1.f - y) * log1pf(-p) + y * logf(p));
-                  df = (fo < lo || fo > hi) ? 0.f : (y / p - (1.f - y) / (1.f - p));
-                } else {
-                  const float res = y - fo;
-                  stat += (double)res * (double)res;
-                  df = res;
-                }
-                dfl[o] = df * act_deriv_from_out<float>(bL.act, fo);
-              }
+            *reinterpret_cast<float4*>(fx_s + (grp * 128 + r) * 4) = make_float4(f[0], f[1], f[2], f[3]);
+            ew_barrier();
+            {
+              const float4 o4 = *reinterpret_cast<const float4*>(fx_s + ((grp ^ 1) * 128 + r) * 4);
+              // fixed order (group 0 + group 1) so both threads of a row get identical bits
+              const float4 m4 = make_float4(f[0], f[1], f[2], f[3]);
+              const float4 a4 = grp == 0 ? m4 : o4, b4 = grp == 0 ? o4 : m4;
+              f[0] = a4.x + b4.x; f[1] = a4.y + b4.y; f[2] = a4.z + b4.z; f[3] = a4.w + b4.w;
             }
-          }
-        }
-        // gradient of the last block (column sums over the tile's rows), dA_{G-1}, dZ_{G-1}
-        {
-          const float* sl = slope_s + (G - 1) * HW;
-#pragma unroll
-          for (int g = 0; g < nH; ++g) {
+            float dfl[4] = {0.f, 0.f, 0.f, 0.f};
+            const float lo = 1e-8f, hi = (float)(1 - 1e-7);          // likelihood.py:229-230
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
               if (o < OUT) {
-                float pr[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) pr[i] = dfl[o] * tu_from_keep<ACTK>(hact, dz[32 * g + i], SLOPES ? sl[32 * g + i] : 0.f);
-                const float cs = colsum32(pr, lane);
-                accl_s[o * HW + 32 * g + lane] += cs;
+                const float fo = act_fwd<float>(bL.act, f[o] + wl_s[OUT * HW + o], 0.f);
+                if (valid) {
+                  const float y = Y[row * (long long)OUT + o];
+                  float df;
+                  if (mp.lik == LIK_BERN) {
+                    const float p = fo < lo ? lo : (fo > hi ? hi : fo);
+                    if (grp == 0) stat += (double)((1.f - y) * log1pf(-p) + y * logf(p));
+                    df = (fo < lo || fo > hi) ? 0.f : (y / p - (1.f - y) / (1.f - p));
+                  } else {
+                    const float res = y - fo;
+                    if (grp == 0) stat += (double)res * (double)res;
+                    df = res;
+                  }
+                  dfl[o] = df * act_deriv_from_out<float>(bL.act, fo);
+                }
               }
             }
-          }
-          float bsum[4];
+            // gradient of the last block (column sums over the tile's rows), dA_{G-1}, dZ_{G-1}
 #pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            float v = dfl[o];
+            for (int g = 0; g < nHH; ++g) {
 #pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
-            bsum[o] = v;
-          }
-          if (lane == 0)
-            for (int o = 0; o < OUT; ++o) accl_s[OUT * HW + o] += bsum[o];
+              for (int o = 0; o < 4; ++o) {
+                if (o < OUT) {
+                  float pr[32];
 #pragma unroll
-          for (int k = 0; k < HW; ++k) {
-            float dA = 0.f;
+                  for (int i = 0; i < 32; ++i) pr[i] = dfl[o] * tu_from_keep<ACTK>(hact, dz[32 * g + i], SLOPES ? sl[32 * g + i] : 0.f);
+                  const float cs = colsum32(pr, lane);
+                  accl_s[o * HW + cb + 32 * g + lane] += cs;
+                }
+              }
+            }
+            if (grp == 0) {
+              float bsum[4];
 #pragma unroll
-            for (int o = 0; o < 4; ++o)
-              if (o < OUT) dA = fmaf(dfl[o], wl_s[o * HW + k], dA);
-            const float sk = dz[k];
-            if (STACKQ) qv[k] = sk < 0.f ? sk * dA : 0.f;
-            dz[k] = dA * tu_deriv<ACTK>(hact, sk, SLOPES ? sl[k] : 0.f);
+              for (int o = 0; o < 4; ++o) {
+                float v = dfl[o];
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+                bsum[o] = v;
+              }
+              if (lane == 0)
+                for (int o = 0; o < OUT; ++o) accl_s[OUT * HW + o] += bsum[o];
+            }
+#pragma unroll
+            for (int k = 0; k < HH; ++k) {
+              float dA = 0.f;
+#pragma unroll
+              for (int o = 0; o < 4; ++o)
+                if (o < OUT) dA = fmaf(dfl[o], wl_s[o * HW + cb + k], dA);
+              const float sk = dz[k];
+              if (STACKQ) qv[STACKQ ? k : 0] = sk < 0.f ? sk * dA : 0.f;
+              dz[k] = dA * tu_deriv<ACTK>(hact, sk, SLOPES ? sl[k] : 0.f);
+            }
           }
         }
         // ------------------------------------------------ backward
@@ -501,131 +529,136 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           // (1) dZ_l as the A operand of B_l (dA_{l-1} = dZ_l W_l): critical path first
           if (l >= 1) {
 #pragma unroll
-            for (int j = 0; j < nH; ++j, ++cc) {
-              const uint32_t st = cc % TU_NS, use = cc / TU_NS;
-              mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
-              put_row_chunk(ringA + st * TU_ASTAGE, r, &dz[32 * j]);
-              publish_A(st);
+            for (int jj = 0; jj < nH; ++jj) {
+              const uint32_t st = slot(cc + jj);
+              if (jj / nHH == grp) put_row_chunk(ringA + st * TU_ASTAGE, r, &dz[32 * (jj % nHH)]);
+              done(st);
             }
+            cc += nH;
           }
-          // (2) drain the previous weight-gradient GEMM (W_{l+1}) before its accumulator is reused
+          // (2) drain the previous weight-gradient GEMM (W_{l+1}): operand row m = TMEM lane = output feature; the two
+          //     column groups split the input features, group 1 also takes the constant-one column (bias, slopes)
           if (l < G - 1) {
             const BlockPlan& bp = mp.b[l + 1];
-            wait_acc(2);
+            wait_acc(1);
             if (r < HW) {
-              float* gw = gout + bp.pw + r * bp.ld_in;
+              float* gw = gout + bp.pw + r * bp.ld_in + cb;
 #pragma unroll 1
-              for (int n0 = 0; n0 < HW; n0 += 16) {
+              for (int n0 = 0; n0 < HH; n0 += 16) {
                 float v[16];
-                umma::tmem_ld16(tbase + lane_t + accCol[2] + n0, v);
+                umma::tmem_ld16(tbase + lane_t + COL_W + cb + n0, v);
                 umma::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) red_add4(gw + n0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
               }
             }
-            {
+            if (grp == 1) {
               float v[8];
-              umma::tmem_ld8(tbase + lane_t + accCol[2] + HW, v);
+              umma::tmem_ld8(tbase + lane_t + COL_W + HW, v);
               umma::tmem_ld_wait();
               if (r < HW) red_add1(gout + bp.pb + r, v[0]);
               else if (STACKQ && act_has_slopes(bp.act)) red_add1(gout + bp.ps + (r - HW), v[0] * sfac_s[(l + 1) * HW + (r - HW)]);
             }
-            umma::fence_before_sync();
-            ew_barrier();
+            free_acc(1);
           }
-          // (3) operands of W_l, chunk `warp` = the 32 rows of this warp
-          {
-            const uint32_t cq = cc + warp, st = cq % TU_NS, use = cq / TU_NS;
-            mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
-            mbar_wait(&bars->emptyB[st], (use & 1u) ^ 1u);
+          // (3) operands of W_l, chunk wq = the 32 rows of this lane quarter; the two column groups split the operand rows
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t st = slot(cc + q);
+            if (q == wq) {
             const uint32_t sa = ringA + st * TU_ASTAGE, sb = ringB + st * tp.b_stage;
 #pragma unroll
-            for (int j = 0; j < HW; ++j) put_t(sa, TU_HALFA, TU_CGA, j, lane, dz[j]);
+            for (int j = 0; j < HH; ++j) put_t(sa, TU_HALFA, TU_CGA, cb + j, lane, dz[j]);
             if (HW == 64) {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) put_t(sa, TU_HALFA, TU_CGA, 64 + j, lane, STACKQ ? qv[STACKQ ? j : 0] : 0.f);
+              for (int j = 0; j < HH; ++j) put_t(sa, TU_HALFA, TU_CGA, 64 + cb + j, lane, STACKQ ? qv[STACKQ ? j : 0] : 0.f);
             }
             if (l >= 1) {
               const int cgs = tu_cgs(NWH), half = tu_half(NWH);
               const float* sc = scr + (size_t)(l - 1) * HW * 128;
-              const float* sl = slope_s + (l - 1) * HW;
-#pragma unroll 4
-              for (int g4 = 0; g4 < HW / 4; ++g4) {
-                const float4 kv = *reinterpret_cast<const float4*>(sc + ((size_t)g4 * 128 + r) * 4);
-                const float k4[4] = {kv.x, kv.y, kv.z, kv.w};
+              const float* sl = slope_s + (l - 1) * HW + cb;
+              float4 kv[HH / 4];
+#pragma unroll
+              for (int g4 = 0; g4 < HH / 4; ++g4) kv[g4] = *reinterpret_cast<const float4*>(sc + ((size_t)(cb / 4 + g4) * 128 + r) * 4);
+#pragma unroll
+              for (int g4 = 0; g4 < HH / 4; ++g4) {
+                const float k4[4] = {kv[g4].x, kv[g4].y, kv[g4].z, kv[g4].w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  put_t(sb, half, cgs, 4 * g4 + i, lane, tu_from_keep<ACTK>(hact, k4[i], SLOPES ? sl[4 * g4 + i] : 0.f));
+                  put_t(sb, half, cgs, cb + 4 * g4 + i, lane, tu_from_keep<ACTK>(hact, k4[i], SLOPES ? sl[4 * g4 + i] : 0.f));
               }
-              put_t(sb, half, cgs, HW, lane, 1.f);
-            } else {
+              if (grp == 1) put_t(sb, half, cgs, HW, lane, 1.f);
+            } else if (grp == 0) {
               const int cgs = tu_cgs(tp.N0w), half = tu_half(tp.N0w);
               for (int k = 0; k < D; ++k) put_t(sb, half, cgs, k, lane, valid ? xrow[k] : 0.f);
               put_t(sb, half, cgs, D, lane, 1.f);
             }
             fence_proxy_async();
-            umma::fence_before_sync();
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive_n(&bars->fullA[st], 4);
-              mbar_arrive(&bars->fullB[st]);
+            if (lane == 0) mbar_arrive(&bars->fullB[st]);
             }
-            cc += 4;
+            done(st);
           }
+          cc += 4;
           // (4) dA_{l-1} from tensor memory -> dZ_{l-1}
           if (l >= 1) {
-            wait_acc(acc);
             const float* sc = scr + (size_t)(l - 1) * HW * 128;
-            const float* sl = slope_s + (l - 1) * HW;
+            const float* sl = slope_s + (l - 1) * HW + cb;
+            float4 kv[HH / 4];
 #pragma unroll
-            for (int j = 0; j < nH; ++j) {
+            for (int g4 = 0; g4 < HH / 4; ++g4) kv[g4] = *reinterpret_cast<const float4*>(sc + ((size_t)(cb / 4 + g4) * 128 + r) * 4);
+            wait_acc(0);
+#pragma unroll
+            for (int j = 0; j < nHH; ++j) {
               float v[32];
-              tmem_ld32(tbase + lane_t + accCol[acc] + 32 * j, v);
+              tmem_ld32(tbase + lane_t + COL_BIG + cb + 32 * j, v);
 #pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 kv = *reinterpret_cast<const float4*>(sc + ((size_t)(8 * j + q4) * 128 + r) * 4);
-                const float k4[4] = {kv.x, kv.y, kv.z, kv.w};
+              for (int i = 0; i < 32; ++i) dz[32 * j + i] = v[i];
+            }
+            free_acc(0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int col = 32 * j + 4 * q4 + i;
-                  const float dA = v[4 * q4 + i];
-                  if (STACKQ) qv[STACKQ ? col : 0] = k4[i] < 0.f ? k4[i] * dA : 0.f;
-                  dz[col] = dA * tu_deriv<ACTK>(hact, k4[i], SLOPES ? sl[col] : 0.f);
-                }
+            for (int g4 = 0; g4 < HH / 4; ++g4) {
+              const float k4[4] = {kv[g4].x, kv[g4].y, kv[g4].z, kv[g4].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int col = 4 * g4 + i;
+                const float dA = dz[col];
+                if (STACKQ) qv[STACKQ ? col : 0] = k4[i] < 0.f ? k4[i] * dA : 0.f;
+                dz[col] = dA * tu_deriv<ACTK>(hact, k4[i], SLOPES ? sl[col] : 0.f);
               }
             }
-            acc ^= 1;
           }
         }
         // ------------------------------------------------ drain W_0
         {
           const BlockPlan& b0 = mp.b[0];
-          wait_acc(2);
-          if (r < HW) {
-            float* gw = gout + b0.pw + r * b0.ld_in;
-            for (int n0 = 0; n0 < tp.N0w; n0 += 8) {
-              float v[8];
-              umma::tmem_ld8(tbase + lane_t + accCol[2] + n0, v);
-              umma::tmem_ld_wait();
+          wait_acc(1);
+          if (grp == 0) {
+            if (r < HW) {
+              float* gw = gout + b0.pw + r * b0.ld_in;
+              for (int n0 = 0; n0 < tp.N0w; n0 += 8) {
+                float v[8];
+                umma::tmem_ld8(tbase + lane_t + COL_W + n0, v);
+                umma::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int n = n0 + i;
-                if (n < D) red_add1(gw + n, v[i]);
-                else if (n == D) red_add1(gout + b0.pb + r, v[i]);
+                for (int i = 0; i < 8; ++i) {
+                  const int n = n0 + i;
+                  if (n < D) red_add1(gw + n, v[i]);
+                  else if (n == D) red_add1(gout + b0.pb + r, v[i]);
+                }
               }
-            }
-          } else if (STACKQ && act_has_slopes(b0.act)) {
-            float v[8];
-            umma::tmem_ld8(tbase + lane_t + accCol[2] + (D & ~7), v);
-            umma::tmem_ld_wait();
-            float pick = 0.f;
+            } else if (STACKQ && act_has_slopes(b0.act)) {
+              float v[8];
+              umma::tmem_ld8(tbase + lane_t + COL_W + (D & ~7), v);
+              umma::tmem_ld_wait();
+              float pick = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i == (D & 7)) pick = v[i];
-            red_add1(gout + b0.ps + (r - HW), pick * sfac_s[r - HW]);
+              for (int i = 0; i < 8; ++i)
+                if (i == (D & 7)) pick = v[i];
+              red_add1(gout + b0.ps + (r - HW), pick * sfac_s[r - HW]);
+            }
           }
-          umma::fence_before_sync();
-          ew_barrier();
+          free_acc(1);
         }
       }
       // ---------------------------------------------------- item epilogue: last block gradient, statistic
@@ -633,7 +666,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       {
         const float* a0 = par + tp.par_accl;
         const int ws = OUT * HW + 4;
-        for (int e = tid; e < OUT * HW; e += 128) {
+        for (int e = tid; e < OUT * HW; e += 256) {
           const int o = e / HW, k = e - o * HW;
           gout[bL.pw + o * bL.ld_in + k] = ((a0[e] + a0[ws + e]) + a0[2 * ws + e]) + a0[3 * ws + e];
         }
@@ -645,15 +678,16 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       {
         double* red = reinterpret_cast<double*>(par + tp.par_accl + 4 * (OUT * HW + 4));
         const double w = warp_sum(stat);
-        if (lane == 0) red[warp] = w;
+        if (lane == 0 && grp == 0) red[wq] = w;
         ew_barrier();
-        if (tid == 0) stat_part[(size_t)c * S + s] = red[0] + red[1] + red[2] + red[3];
+        if (tid == 0) stat_part[(size_t)c * S + s] = ((red[0] + red[1]) + red[2]) + red[3];
       }
     }
   }
+  __syncwarp();
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 4) umma::tmem_dealloc(tbase, 512);
+  if (warp == TU_MMA_WARP) umma::tmem_dealloc(tbase, 512);
 }
 
 // ------------------------------------------------------------------ host side
@@ -696,7 +730,8 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   tp.par_slope = pf; pf += G * HW;
   tp.par_sraw = pf; pf += G * HW;
   tp.par_wl = pf; pf += mp.OUT * HW + 4;
-  tp.par_accl = pf; pf += 4 * (mp.OUT * HW + 4) + 16;    // one per row-worker warp, + 8 doubles of reduction scratch
+  tp.par_accl = pf; pf += 4 * (mp.OUT * HW + 4) + 16;    // one per lane quarter, + 8 doubles of reduction scratch
+  tp.par_fx = pf; pf += 2 * 128 * 4;
   off += pf * 4;
   off = tu_pad(off, 16);
   tp.off_bar = off; off += (int)sizeof(TuBars);
