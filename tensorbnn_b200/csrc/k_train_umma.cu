@@ -117,7 +117,7 @@ __global__ void k_train_prep(const __grid_constant__ ModelPlan mp, const __grid_
   }
   float hi[4], lo[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) umma::split_tf32(v[i], hi[i], lo[i]);
+  for (int i = 0; i < 4; ++i) umma::split_tf32_fast(v[i], hi[i], lo[i]);
   const int cgs = tu_cgs(HW);
   unsigned char* base = wimg + (size_t)c * tp.wimg_chain + (bwd ? tp.bimg[l] : tp.fimg[l]) + (size_t)chunk * 2 * tu_half(HW);
   const int off = (n >> 3) * 128 + kq * cgs + (n & 7) * 16;
@@ -152,7 +152,7 @@ __device__ __forceinline__ void put_row_chunk(uint32_t stage, int r, const float
   for (int kq = 0; kq < 8; ++kq) {
     float h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) umma::split_tf32(v[4 * kq + i], h[i], l[i]);
+    for (int i = 0; i < 4; ++i) umma::split_tf32_fast(v[4 * kq + i], h[i], l[i]);
     const uint32_t a = stage + kq * TU_CGA + r * 16;
     sts128(a, h[0], h[1], h[2], h[3]);
     sts128(a + TU_HALFA, l[0], l[1], l[2], l[3]);
@@ -161,7 +161,7 @@ __device__ __forceinline__ void put_row_chunk(uint32_t stage, int r, const float
 // one value of the transposed (K = rows) operand: operand row n, k = lane, column-group stride cgs
 __device__ __forceinline__ void put_t(uint32_t stage, int half, int cgs, int n, int lane, float v) {
   float h, l;
-  umma::split_tf32(v, h, l);
+  umma::split_tf32_fast(v, h, l);
   const uint32_t a = stage + (n >> 3) * 128 + (lane >> 2) * cgs + (n & 7) * 16 + (lane & 3) * 4;
   sts32(a, h);
   sts32(a + half, l);
@@ -263,7 +263,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       // one GEMM of `nch` chunks with `ks` (last chunk: ks_last) k steps into accumulator region `acc` (0: F / B, 1: W);
       // split: the lo*hi and hi*lo products go to their own accumulator (forward GEMMs)
       auto gemm = [&](int nch, int ks_last, uint32_t idesc, int cgsB, int acc, bool split) {
-        mbar_wait(&bars->accfree[acc], (accuse[acc] & 1u) ^ 1u);
+        mbar_wait_parked(&bars->accfree[acc], (accuse[acc] & 1u) ^ 1u);
         accuse[acc]++;
         umma::fence_after_sync();
         const uint32_t dbig = umma::tmem_addr(tbase, 0, acc == 0 ? COL_BIG : COL_W);
@@ -271,8 +271,8 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         const uint32_t halfB = 8u * cgsB;
         for (int ch = 0; ch < nch; ++ch, ++cc) {
           const uint32_t st = cc % TU_NS, use = cc / TU_NS;
-          mbar_wait(&bars->fullA[st], use & 1u);
-          mbar_wait(&bars->fullB[st], use & 1u);
+          mbar_wait_parked(&bars->fullA[st], use & 1u);
+          mbar_wait_parked(&bars->fullB[st], use & 1u);
           umma::fence_after_sync();
           const uint32_t a0 = ringA + st * TU_ASTAGE, b0 = ringB + st * tp.b_stage;
           const int ks = ch == nch - 1 ? ks_last : 4;
@@ -325,7 +325,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
     float* scr = scratch + (size_t)blockIdx.x * tp.scratch_cta;
 
     auto wait_acc = [&](int a) {
-      mbar_wait(&bars->accfull[a], accuse[a] & 1u);
+      mbar_wait_parked(&bars->accfull[a], accuse[a] & 1u);
       accuse[a]++;
       umma::fence_after_sync();
     };
@@ -340,7 +340,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
     // ring-B slot is the same event (the MMA issuer commits both), so ring B needs no wait of its own here.
     auto slot = [&](uint32_t cq) -> uint32_t {
       const uint32_t st = cq % TU_NS, use = cq / TU_NS;
-      mbar_wait(&bars->emptyA[st], (use & 1u) ^ 1u);
+      mbar_wait_parked(&bars->emptyA[st], (use & 1u) ^ 1u);
       return st;
     };
     auto done = [&](uint32_t st) {
@@ -395,7 +395,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
               for (int i = 0; i < 4; ++i) {
                 const int k = 32 * ch + 4 * kq + i;
                 const float x = (valid && k < D) ? xrow[k] : 0.f;
-                umma::split_tf32(x, h[i], l4[i]);
+                umma::split_tf32_fast(x, h[i], l4[i]);
               }
               const uint32_t a = stage + kq * TU_CGA + r * 16;
               sts128(a, h[0], h[1], h[2], h[3]);

@@ -134,6 +134,15 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = rn_tf32(x - hi);
 }
 
+// Split without conversion instructions (cvt.rna.tf32 issues at a fraction of the ALU rate): both parts rounded to
+// nearest TF32 with integer arithmetic -- add half an ulp of the 10-bit mantissa, clear the low 13 bits (ties away from
+// zero; a carry into the exponent is the correct next binade).  Five full-rate instructions; |lo| <= 2^-12 |x| with
+// either sign, so the dropped lo*lo product (<= 2^-24 |a b|) does not pile up one-sidedly.
+__device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+}
+
 // cheaper split for forward-only use (posterior-predictive sweep): hi = truncation (what the tensor core does to
 // its operands anyway), lo = exact remainder, truncated again by the hardware -> one-sided error ~2^-21 |x| per
 // product, irrelevant next to Monte Carlo error; two ALU instructions instead of two conversions and a subtract
