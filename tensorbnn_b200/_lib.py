@@ -18,6 +18,7 @@ FLAG_NO_UMMA = 2   # tbnn_desc.flags: never use the tcgen05 (tensor-core) kernel
 FLAG_NO_WIDE2 = 4  # tbnn_desc.flags: phase-serial wide sweep instead of the warp-specialised one
 FLAG_NO_PERSISTENT = 16  # tbnn_desc.flags: never run a trajectory as one persistent launch (k_traj_small)
 FLAG_NO_NARROW = 32  # tbnn_desc.flags: persistent trajectories on the tile engine only (no k_traj_narrow)
+FLAG_NO_UMMA_TRAIN = 64  # tbnn_desc.flags: hidden-layer GEMMs of the training sweep on FP32 FFMA (k_partial), not tcgen05
 FLAG_UMMA_SWEEP = 8  # tbnn_desc.flags: wide-first-layer sweep on tcgen05 (k_sweep_umma) instead of FP32 FFMA2 (opt-in)
 
 EXPORTS = ["tbnn_last_error", "tbnn_version", "tbnn_create", "tbnn_destroy", "tbnn_num_params",
