@@ -1,19 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- chain-leapfrog-steps/sec of the B200 HMC hot path (BASELINE.json metric).
 
-One bench "step" = one HMC transition of the main chain through the C ABI (tbnn_hmc_step:
-momentum draw, bootstrap gradient, L leapfrog steps each with ONE full-data log-posterior +
-gradient evaluation, Metropolis select).  value = ranks * chains * L * K / device time.
+One bench "step" = one HMC transition of every chain of the workload through the C ABI (tbnn_hmc_step: momentum draw,
+bootstrap gradient, L leapfrog steps each with ONE full-data log-posterior + gradient evaluation, Metropolis select).
+value = chains * L * K / device time (max over ranks).
 
-Workload at N=1: C2 = BASELINE.json configs[1] (docs ClassificationExample shape): 9,600 x 784
-synthetic 2-class data, 784-20-20-1 ReLU/ReLU/Sigmoid, DenseLayer (Cauchy) priors,
-BernoulliLikelihood, one chain, fixed L = 500, eps = 1e-3.  N>1: one independent chain per GPU
-(chains split with no communication -> "weak" scaling).
+Default workload: **C3** = BASELINE.json configs[2], the batched-chain shape the metric is quoted on ("chain-
+leapfrog-steps/sec at 1/2/4/8 B200"): 1,024 independent chains of a 1-64-64-64-1 SquarePrelu network on 4,096 rows,
+GaussianLikelihood, L = 100.  It fits one GPU; with --gpus N the 1,024 chains are split 1024/N per GPU with no
+communication ("strong" scaling: the total work is fixed).  Other shapes: --workload c1 | c2 | c2l | c4 | c5
+(c4 at N > 1: training rows sharded, one NCCL all-reduce per gradient evaluation).
 
   python bench.py --gpus N --steps K --warmup W            # this framework
-  python bench.py --impl reference ...                     # the reference-equivalent CPU port
+  python bench.py --impl reference ...                     # the reference's CPU path (oracle port, all host threads)
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -32,6 +34,7 @@ from tensorbnn_b200 import workloads as wl
 
 METRIC = "chain-leapfrog-steps/sec"
 UNIT = "leapfrog-steps/s"
+DEFAULT_WORKLOAD = "c3"
 
 
 def load_peaks():
@@ -43,13 +46,17 @@ def load_peaks():
 
 
 def ncu_traffic(kernel, workload):
-    """dram read + write bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the
-    same workload (profiles/), or None.  Cold-cache figure: in steady state C2's 30 MB set is L2-resident."""
-    if workload != "c2" or kernel != "k_sweep_wide2":
+    """dram read + write bytes per launch of the dominant kernel from the newest committed `ncu --set full` capture of
+    the same workload (profiles/*_<kernel>_<workload>_full_metrics.csv, raw page), or None."""
+    short = {"k_sweep_wide2": "wide2", "k_train_umma": "train_umma", "k_partial": "partial", "k_predict_umma": "predict_umma"}.get(kernel, kernel)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_%s_%s_full_metrics.csv" % (short, workload))))
+    if not files and workload == "c2":
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_%s_full_metrics.csv" % short)))
+    if not files:
         return None
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1e_wide2_full_metrics.csv"))))
+        rows = list(csv.reader(open(files[-1])))
         hdr, units, vals = rows[0], rows[1], rows[2]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tot = 0.0
@@ -61,28 +68,53 @@ def ncu_traffic(kernel, workload):
         return None
 
 
-def make_workload(name, rank=0):
+def make_workload(name, rank=0, world=1):
+    """(cfg, theta [C_local, P], hyper [C_local, H], first global chain index).  Chains are split across ranks."""
     if name == "c2":
         cfg = wl.c2()
     elif name == "c2l":
-        cfg = wl.c2(N=1048576 // 4)
-        cfg["name"] = "C2-L/4"
+        cfg = wl.c2(N=1048576)
+        cfg["name"] = "C2-L"
     elif name == "c1":
         cfg = wl.c1("a")
     elif name == "c3":
-        cfg = wl.c3(chains=148 * 2)
+        cfg = wl.c3(chains=1024)
     elif name == "c4":
         cfg = wl.c4()
     else:
         raise ValueError(name)
-    C = cfg["chains"]
+    C_total = cfg["chains"]
+    if C_total >= world and name == "c3":
+        lo, hi = C_total * rank // world, C_total * (rank + 1) // world     # strong scaling over chains
+    else:
+        lo, hi = rank * C_total, (rank + 1) * C_total                       # one replica of the chain set per rank
     arch, lik = cfg["arch"], cfg["lik"]
-    theta = np.stack([wl.init_theta(arch, seed=1000 * rank + c, slope=cfg.get("slope", 0.2)) * cfg.get("wscale", 1.0)
-                      for c in range(C)])
+    theta = np.stack([wl.init_theta(arch, seed=1000 + c, slope=cfg.get("slope", 0.2)) * cfg.get("wscale", 1.0)
+                      for c in range(lo, hi)])
     if name in ("c2", "c2l"):
         theta = theta * 0.2   # moderate logits at the random start (see tests/test_gpu_parity.py)
-    hyper = np.tile(wl.init_hyper(arch, lik), (C, 1))
-    return cfg, theta, hyper
+    hyper = np.tile(wl.init_hyper(arch, lik), (hi - lo, 1))
+    cfg["chains_total"] = C_total if name == "c3" else C_total * world
+    cfg["chains"] = hi - lo
+    return cfg, theta, hyper, lo
+
+
+def config_dict(cfg, L, eps, world, rows_sharded):
+    """The `config` object of the JSON line; the reference arm prints the identical object."""
+    arch, lik = cfg["arch"], cfg["lik"]
+    name = cfg["name"]
+    if rows_sharded:
+        par = "one chain, training rows sharded %d ways, one NCCL all-reduce of the partial gradient per gradient evaluation" % world
+    elif name == "C3":
+        par = "%d chains split %d per GPU, no communication" % (cfg["chains_total"], cfg["chains_total"] // max(world, 1))
+    else:
+        par = "one chain per GPU, no communication" if world > 1 else "single chain"
+    return {"workload": name, "rows": int(cfg["rows_total"]), "features": int(cfg["X"].shape[1]),
+            "network": "-".join(str(d) for d in [arch[0][1]] + [l[2] for l in arch if l[0].startswith("dense")]),
+            "activation": [l[0] for l in arch if not l[0].startswith("dense")][0],
+            "likelihood": lik[0], "chains": int(cfg["chains_total"]), "leapfrog_per_step": int(L),
+            "parallelism": par,
+            "l2": "flushed between timed steps (256 MB write); within a trajectory the working set stays L2-resident"}
 
 
 class ClockSampler(object):
@@ -143,40 +175,61 @@ def flops_per_chain_step(cfg):
     return cfg["X"].shape[0] * (6 * F - 2 * dims[0][1] * dims[0][2])
 
 
+def cpu_sample(name, cfg):
+    """Bounded sample of the workload for the CPU arm: (X, Y, scale, text).  One CPU chain-leapfrog-step on the sample
+    costs `scale` of one on the full workload (the cost is linear in rows); chains are identical in cost."""
+    X, Y = cfg["X"], np.asarray(cfg["Y"])
+    rows = {"c4": 262144, "c2l": 65536}.get(name)
+    if rows and rows < len(X):
+        frac = rows / float(len(X))
+        return X[:rows], Y[:rows], frac, "a %d-row slice (1/%d of the rows; throughput scaled by %g, the cost is linear in rows)" % (
+            rows, len(X) // rows, frac)
+    if name == "c3":
+        return X, Y, 1.0, "one of the %d chains on all %d rows (chains cost the same; they would run one after another)" % (
+            cfg["chains_total"], len(X))
+    return X, Y, 1.0, "the full workload"
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path: TF/TFP cannot be installed offline, so this is
-    the oracle port (reference-equivalent torch-CPU restatement), all host threads."""
+    """The reference's CPU implementation of the path.  TF/TFP cannot be installed offline, so this is the oracle port
+    (reference op structure restated on torch-CPU: per-layer W@A+b, separate activation op, autograd backward,
+    TFP-ordered leapfrog), all host threads.  One step = one L-step trajectory (the workload's own L) on a bounded
+    sample of the workload; same metric / unit / config as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cpu_baseline
-    cfg, theta, hyper = make_workload(args.workload)
-    cores = os.cpu_count() or 1
-    L_s = args.ref_leapfrog
-    times = []
-    torch.set_num_threads(cores)
     from oracle import hmc
+    cfg, theta, hyper, _ = make_workload(args.workload, 0, 1)
+    cfg["rows_total"] = cfg["X"].shape[0]
+    if args.workload == "c3":
+        cfg["chains_total"] = 1024
+    elif args.workload != "c4":
+        cfg["chains_total"] = cfg["chains_total"] * max(args.gpus, 1)
+    L = args.leapfrog or cfg["L"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Xs, Ys, scale, text = cpu_sample(args.workload, cfg)
     f32 = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32)
-    vg = hmc.make_main_vg(cfg["arch"], cfg["lik"], f32(hyper[0]), f32(cfg["X"]), f32(cfg["Y"]))
+    vg = hmc.make_main_vg(cfg["arch"], cfg["lik"], f32(hyper[0]), f32(Xs), f32(Ys))
     g = torch.Generator().manual_seed(0)
     th = f32(theta[0])
+    times = []
     for i in range(args.warmup + args.steps):
         p = torch.randn(th.shape, generator=g)
         t0 = time.perf_counter()
-        hmc.leapfrog(vg, th, p, cfg["eps"], L_s)
+        hmc.leapfrog(vg, th, p, cfg["eps"], L if i >= args.warmup else min(L, 5))
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
     total = sum(times)
-    value = L_s * len(times) / total
-    sample = "%d-leapfrog-step trajectories of the full %s workload per step (bootstrap gradient included)" % (
-        L_s, cfg["name"])
+    value = scale * L * len(times) / total
+    sample = "per step one %d-leapfrog-step trajectory (bootstrap gradient included) of %s" % (L, text)
+    rows_sharded = args.workload == "c4" and args.gpus > 1
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": cfg["name"], "rows": int(cfg["X"].shape[0]), "features": int(cfg["X"].shape[1]),
-                       "chains": 1, "leapfrog_per_step": L_s},
+            "higher_is_better": True, "scaling": "strong" if (args.workload in ("c3", "c4")) else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(cfg, L, cfg["eps"], max(args.gpus, 1), rows_sharded),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -292,16 +345,35 @@ def _stdout_to_stderr():
     return restore
 
 
+def tune_step_size(eng, th, hy, eps0, L, rank):
+    """Per-chain step sizes at which the chains move: halve a chain's step size until a short trajectory is accepted
+    with probability >= 0.5 (the reference tunes the step size as well, with its paramAdapter)."""
+    C = th.shape[0]
+    eps = np.full(C, float(eps0))
+    stats = torch.zeros(C, 4, dtype=th.dtype, device=th.device)
+    Lt = max(2, min(L, 10))
+    for it in range(24):
+        trial = th.clone()
+        eng.hmc_step(trial, hy, 77 + rank, 1000 + it, eps, Lt, stats=stats)
+        acc = stats[:, 1].cpu().numpy()
+        bad = ~(acc >= 0.5)
+        if not bad.any():
+            break
+        eps[bad] *= 0.5
+    return eps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--leapfrog", type=int, default=0, help="override L (0 = workload default)")
-    ap.add_argument("--ref-leapfrog", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tune", action="store_true", help="keep the workload's nominal step size")
+    ap.add_argument("--flags", type=int, default=0, help="TBNN_FLAG_* for the engine (64 = FFMA tile engine instead of tcgen05)")
     ap.add_argument("--pred-samples", type=int, default=512, help="c5: stored samples per GPU and step")
     ap.add_argument("--pred-rows", type=int, default=1048576, help="c5: test rows")
     args = ap.parse_args()
@@ -322,13 +394,16 @@ def main():
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
     from tensorbnn_b200.engine import Engine
-    cfg, theta, hyper = make_workload(args.workload, rank)
+    rows_sharded = args.workload == "c4" and world > 1
+    cfg, theta, hyper, chain0 = make_workload(args.workload, 0 if rows_sharded else rank, 1 if rows_sharded else world)
+    if rows_sharded:
+        cfg["chains_total"] = 1
+    cfg["rows_total"] = cfg["X"].shape[0]
     arch, lik, C = cfg["arch"], cfg["lik"], cfg["chains"]
     L = args.leapfrog or cfg["L"]
-    eps = cfg["eps"]
     dt = torch.float32
-    eng = Engine(arch, lik, dtype=dt, chains=C, device=local_rank)
-    rows_sharded = args.workload == "c4" and world > 1
+    eng = Engine(arch, lik, dtype=dt, chains=C, device=local_rank, flags=args.flags)
+    seed = 1 if rows_sharded else 1 + rank
     if rows_sharded:
         # one chain, training rows split across the ranks, one NCCL all-reduce of the partial gradient per
         # gradient evaluation inside libtbnn.so; every rank replays the identical chain
@@ -349,18 +424,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput ("value")
+    # ---------------- step sizes at which the chains move (untimed), then warm-up
+    eps = np.full(C, float(cfg["eps"])) if args.no_tune else tune_step_size(eng, th, hy, cfg["eps"], L, 0 if rows_sharded else rank)
     for i in range(args.warmup):
-        eng.hmc_step(th, hy, 1 + (0 if rows_sharded else rank), i, eps, L, stats=stats)
+        eng.hmc_step(th, hy, seed, i, eps, L, stats=stats)
+    # ---------------- device-resident throughput ("value")
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
     launches0 = eng.launches
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    acc_sum = 0.0
     for i in range(args.steps):
         flush.zero_()                                   # evict L2 between timed iterations
         evs[i][0].record()
-        eng.hmc_step(th, hy, 1 + (0 if rows_sharded else rank), args.warmup + i, eps, L, stats=stats)
+        eng.hmc_step(th, hy, seed, args.warmup + i, eps, L, stats=stats)
         evs[i][1].record()
     barrier()
     gpu_launches = eng.launches - launches0
@@ -370,12 +448,13 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
-    units = 1 if rows_sharded else world          # row sharding: ONE chain advanced by all ranks together
-    value = units * C * L * args.steps / (dev_ms * 1e-3)
+    units = 1 if rows_sharded else cfg["chains_total"]          # chains advanced by all ranks together
+    value = units * L * args.steps / (dev_ms * 1e-3)
     accept = float(stats[:, 1].mean().item())
+    moved = float((stats[:, 2] > 0).float().mean().item())
 
     # ---------------- end to end through the C ABI with HOST buffers
-    th_h = torch.tensor(theta, dtype=dt).contiguous().pin_memory()
+    th_h = th.detach().cpu().contiguous().pin_memory()
     hy_h = torch.tensor(hyper, dtype=dt).contiguous().pin_memory()
     th_o = torch.empty_like(th_h).pin_memory()
     st_o = torch.zeros(C, 4, dtype=dt).pin_memory()
@@ -387,7 +466,7 @@ def main():
         eng.set_data_host(Xh, Yh)                       # training set from pinned host memory
         th.copy_(th_h, non_blocking=True)
         hy.copy_(hy_h, non_blocking=True)
-        eng.hmc_step(th, hy, 1 + (0 if rows_sharded else rank), 10_000 + i, eps, L, stats=stats)
+        eng.hmc_step(th, hy, seed, 10_000 + i, eps, L, stats=stats)
         th_o.copy_(th, non_blocking=True)
         st_o.copy_(stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -404,49 +483,62 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = units * C * L * e2e_steps / float(t.item())
+    e2e_value = units * L * e2e_steps / float(t.item())
     eng.set_data(Xh.cuda(), Yh.cuda())
 
     # ---------------- roofline of the dominant kernel (row sweep), CUDA events inside the library
     peaks, peak_src = load_peaks()
-    avg_ms, min_ms = eng.time_sweep(th, iters=50)
+    avg_ms, min_ms = eng.time_sweep(th, iters=20 if avg_guess(cfg, C) else 50)
+    info = eng.sweep_info()
     abytes = algorithmic_bytes_per_step(cfg, eng.P, 4, C)
-    achieved = abytes / (avg_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(eng.sweep_info()["kernel"], args.workload),
-            "kernel": eng.sweep_info()["kernel"], "sweep": eng.sweep_info(),
-            "launch_ms": avg_ms, "launch_ms_min": min_ms, "algorithmic_bytes_per_launch": abytes,
-            "peak_source": peak_src,
-            "fp32_tflops": C * flops_per_chain_step(cfg) / (avg_ms * 1e-3) / 1e12,
-            "note": "C2's 30 MB working set is L2-resident across the leapfrog steps of a trajectory "
-                    "(the real access pattern); FP32 FFMA also bounds this shape (SURVEY 8d)"}
+    hbm_gbs = abytes / (avg_ms * 1e-3) / 1e9
+    tflops = C * flops_per_chain_step(cfg) / (avg_ms * 1e-3) / 1e12
+    tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2 / 3
+    ffma_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    roof = {"kernel": info["kernel"], "sweep": info, "launch_ms": avg_ms, "launch_ms_min": min_ms,
+            "share_of_step": avg_ms * (L + 1) * args.steps / dev_ms,
+            "traffic": ncu_traffic(info["kernel"], args.workload), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": abytes, "algorithmic_flops_per_launch": C * flops_per_chain_step(cfg),
+            "hbm_gbs": hbm_gbs, "hbm_frac": hbm_gbs / peaks["hbm_gbs"], "fp32_equivalent_tflops": tflops,
+            "ffma_frac": tflops / ffma_peak}
+    if info["kernel"] == "k_train_umma":
+        roof.update({"bound": "tensor", "achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak,
+                     "note": "useful fp32-equivalent flops N(6F - 2 d0 d1) per chain-step (SURVEY 8d); peak = measured sustained "
+                             "bf16 dense / 2 (tf32) / 3 (3xTF32 issues three MMAs per product).  HBM and FP32-FFMA fractions "
+                             "alongside (hbm_frac, ffma_frac)."})
+    else:
+        roof.update({"bound": "hbm", "achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
+                     "note": "algorithmic bytes N(d0+dK)s + 4Ps per launch (SURVEY 8d); small working sets are L2-resident across "
+                             "the leapfrog steps of a trajectory; FP32 FFMA also bounds the wide-first-layer shape (ffma_frac); "
+                             "C1 is latency-bound (one tile), no roofline fraction is meaningful there."})
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---------------- CPU baseline beside it (rank 0, N=1 only)
+    # ---------------- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline
+        Xs, Ys, scale, text = cpu_sample(args.workload, cfg)
+        Lc = min(L, 20)
         v, nsteps, cores = cpu_baseline.leapfrog_steps_per_second(
-            arch, lik, cfg["X"], cfg["Y"], theta[0], hyper[0], eps, 20, min_seconds=10.0)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d leapfrog steps of the full %s workload in 20-step trajectories, torch-CPU fp32 "
-                         "restatement of the reference (TensorFlow unavailable offline)" % (nsteps, cfg["name"])}
+            arch, lik, Xs, Ys, theta[0], hyper[0], cfg["eps"], Lc, min_seconds=10.0)
+        cpu = {"value": v * scale, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d leapfrog steps in %d-step trajectories of %s; torch-CPU fp32 restatement of the reference's op "
+                         "sequence (TensorFlow cannot be installed offline)" % (nsteps, Lc, text)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if rows_sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "rows": int(cfg["X"].shape[0]), "features": int(cfg["X"].shape[1]),
-                       "network": "-".join(str(d) for d in [arch[0][1]] + [l[2] for l in arch if l[0].startswith("dense")]),
-                       "likelihood": lik[0], "chains_per_gpu": C, "leapfrog_per_step": L, "step_size": eps,
-                       "parallelism": ("rows sharded, one NCCL all-reduce per gradient evaluation" if rows_sharded else
-                                       "chains split, no communication" if world > 1 else "single chain"),
-                       "l2": "flushed between timed steps (256 MB write); within a trajectory the data is L2-resident"},
+            "scaling": "strong" if (rows_sharded or args.workload == "c3") else "weak", "vs_baseline": None,
+            "dtype": "f32 (hidden-layer GEMMs: 3xTF32 on tcgen05)" if info["kernel"] == "k_train_umma" else "f32",
+            "data": "synthetic",
+            "config": config_dict(cfg, L, cfg["eps"], world, rows_sharded),
+            "step_size": {"nominal": float(cfg["eps"]), "median_used": float(np.median(eps)), "min_used": float(eps.min()),
+                          "how": "per-chain halving until a 10-step trajectory is accepted with probability >= 0.5"},
             "us_per_leapfrog": 1e3 * dev_ms / (args.steps * L),
-            "accept_prob_last": accept,
+            "accept_prob_last": accept, "accepted_fraction_last": moved,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps,
                     "what": "per step: tbnn_set_data_host(X,Y) + theta/hyper H2D + tbnn_hmc_step + theta/stats D2H"},
@@ -457,6 +549,11 @@ def main():
     sys.stdout.flush()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def avg_guess(cfg, C):
+    """True for workloads whose sweep takes milliseconds (fewer timing iterations suffice)."""
+    return cfg["X"].shape[0] * C >= (1 << 20)
 
 
 if __name__ == "__main__":

@@ -428,7 +428,19 @@ static int after_data(tbnn_handle* h, long long n_rows, cudaStream_t st = 0) {
     const int s_tile = (int)((ntile + q - 1) / q);
     h->use_usweep = h->want_usweep && plan_usweep(h->mp, n_rows, s_row, SMEM_LIMIT, h->uw, h->up);
     h->S = (h->use_wide || h->use_usweep) ? s_row : s_tile;
-    h->S_tu = (int)std::max<long long>(1, std::min<long long>(smax, (n_rows + 127) / 128));
+    {
+      // persistent grid of num_sms CTAs over C * S work items of ceil(ntile / S) 128-row tiles each: pick the S with the
+      // smallest makespan (a quarter tile of per-item overhead: parameters, zeroing and writing the partial slice)
+      const long long nt128 = (n_rows + 127) / 128;
+      double best = 1e300;
+      int bestS = 1;
+      for (long long S = 1; S <= std::min<long long>(nt128, h->num_sms); ++S) {
+        const long long waves = ((long long)h->C * S + h->num_sms - 1) / h->num_sms;
+        const double cost = (double)waves * ((double)((nt128 + S - 1) / S) + 0.25);
+        if (cost < best * (1.0 - 1e-9)) { best = cost; bestS = (int)S; }
+      }
+      h->S_tu = bestS;
+    }
     if (h->use_tu) h->S = h->S_tu;   // one partial count for the sweep, the forward-only statistic sweep and finalize
   }
   const size_t need = (size_t)h->C * h->S * h->mp.Ppad * h->esz;
