@@ -137,7 +137,7 @@ class Prelu(_SlopeActivation):
         _SlopeActivation.__init__(self, inputDims, outputDims, dtype, alpha, activation, seed)
         self.numHyperTensors = 1
         self.hyperRate = 0.3
-        self.hypers = [torch.tensor(0.3, dtype=self.tdtype)]
+        self.hypers = [torch.tensor(0.3, dtype=torch.float32).to(self.tdtype)]      # tf.cast(0.3, dtype): float32 first (Q14)
 
     def exponentialLogProb(self, rate, x):
         rate = abs(float(rate))
@@ -167,7 +167,7 @@ class SquarePrelu(_SlopeActivation):
     def __init__(self, inputDims, outputDims=None, dtype=np.float32, alpha=0.2, activation=None, seed=1):
         _SlopeActivation.__init__(self, inputDims, outputDims, dtype, alpha, activation, seed)
         self.numHyperTensors = 2
-        self.hypers = [torch.tensor(0.0, dtype=self.tdtype), torch.tensor(0.3, dtype=self.tdtype)]
+        self.hypers = [torch.tensor(0.0, dtype=self.tdtype), torch.tensor(0.3, dtype=torch.float32).to(self.tdtype)]   # Q14
 
     @staticmethod
     def _mvlp(sd, mean, x):

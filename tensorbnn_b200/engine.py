@@ -13,8 +13,8 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class Engine(object):
@@ -32,7 +32,7 @@ class Engine(object):
             raise ValueError("dtype must be float32 or float64")
         desc, self._keep = _lib.make_desc(self.arch, self.lik, code, self.chains, self.device, flags)
         h = C.c_void_p()
-        _lib.check(self.lib.tbnn_create(C.byref(desc), C.byref(h)))
+        self._call(self.lib.tbnn_create, (C.byref(desc), C.byref(h)))
         self.h = h
         self.P = self.lib.tbnn_num_params(h)
         self.H = self.lib.tbnn_num_hypers(h)
@@ -48,6 +48,16 @@ class Engine(object):
             pass
 
     # ------------------------------------------------------------------ helpers
+    def _st(self):
+        """torch's current stream ON THIS ENGINE'S DEVICE (a stream handle of another device is invalid there)."""
+        return _stream(self.device)
+
+    def _call(self, fn, args):
+        """Library call with this engine's device current: every tbnn_* entry point does cudaSetDevice(handle device),
+        so without the guard a handle on device k would leave the thread's CUDA device changed behind torch's back."""
+        with torch.cuda.device(self.device):
+            _lib.check(fn(*args))
+
     def tensor(self, a, shape=None):
         t = torch.as_tensor(np.asarray(a), dtype=self.dtype).to(self.dev).contiguous() \
             if not isinstance(a, torch.Tensor) else a.to(self.dev, self.dtype).contiguous()
@@ -64,13 +74,13 @@ class Engine(object):
     def sweep_info(self):
         """dict(kernel=..., ctas_per_chain=..., rows_per_tile=..., smem_bytes=...) of the planned row sweep."""
         k, s, r, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        _lib.check(self.lib.tbnn_sweep_info(self.h, C.byref(k), C.byref(s), C.byref(r), C.byref(b)))
+        self._call(self.lib.tbnn_sweep_info, (self.h, C.byref(k), C.byref(s), C.byref(r), C.byref(b)))
         return {"kernel": ["k_partial", "k_sweep_wide", "k_sweep_wide2", "k_sweep_umma", "k_train_umma"][k.value], "ctas_per_chain": s.value,
                 "rows_per_tile": r.value, "smem_bytes": b.value}
 
     def predict_kernel(self):
         k = C.c_int()
-        _lib.check(self.lib.tbnn_predict_info(self.h, C.byref(k)))
+        self._call(self.lib.tbnn_predict_info, (self.h, C.byref(k)))
         return ["k_predict", "k_predict_umma"][k.value]
 
     # ------------------------------------------------------------------ data
@@ -81,14 +91,14 @@ class Engine(object):
         X = X.reshape(self.N, -1)
         Y = Y.reshape(self.N, -1)
         self._data = (X, Y)
-        _lib.check(self.lib.tbnn_set_data(self.h, _ptr(X), _ptr(Y), self.N))
+        self._call(self.lib.tbnn_set_data, (self.h, _ptr(X), _ptr(Y), self.N))
 
     def set_data_host(self, X_host, Y_host):
         """X_host / Y_host: CPU tensors (pinned for an async copy) of the engine dtype."""
         assert X_host.dtype == self.dtype and Y_host.dtype == self.dtype and not X_host.is_cuda
         self.N = X_host.shape[0]
         self._data = (X_host, Y_host)
-        _lib.check(self.lib.tbnn_set_data_host(self.h, _ptr(X_host), _ptr(Y_host), self.N, _stream()))
+        self._call(self.lib.tbnn_set_data_host, (self.h, _ptr(X_host), _ptr(Y_host), self.N, self._st()))
 
     # ------------------------------------------------------------------ targets
     def logp_grad(self, theta, hyper):
@@ -97,8 +107,8 @@ class Engine(object):
         logp = torch.empty(self.chains, dtype=self.dtype, device=self.dev)
         grad = torch.empty(self.chains, self.P, dtype=self.dtype, device=self.dev)
         stat = torch.empty(self.chains, dtype=self.dtype, device=self.dev)
-        _lib.check(self.lib.tbnn_logp_grad(self.h, _ptr(theta), _ptr(hyper), _ptr(logp), _ptr(grad),
-                                           _ptr(stat), _stream()))
+        self._call(self.lib.tbnn_logp_grad, (self.h, _ptr(theta), _ptr(hyper), _ptr(logp), _ptr(grad),
+                                           _ptr(stat), self._st()))
         return logp, grad, stat
 
     def hyper_logp_grad(self, theta, hyper, sse=None):
@@ -107,8 +117,8 @@ class Engine(object):
         sse_t = self.tensor(sse, (self.chains,)) if sse is not None else None
         logp = torch.empty(self.chains, dtype=self.dtype, device=self.dev)
         grad = torch.empty(self.chains, self.H, dtype=self.dtype, device=self.dev)
-        _lib.check(self.lib.tbnn_hyper_logp_grad(self.h, _ptr(theta), _ptr(hyper), _ptr(sse_t),
-                                                 _ptr(logp), _ptr(grad), _stream()))
+        self._call(self.lib.tbnn_hyper_logp_grad, (self.h, _ptr(theta), _ptr(hyper), _ptr(sse_t),
+                                                 _ptr(logp), _ptr(grad), self._st()))
         return logp, grad
 
     # ------------------------------------------------------------------ sampler
@@ -121,8 +131,8 @@ class Engine(object):
         g = torch.empty_like(theta)
         lp = torch.empty(self.chains, dtype=self.dtype, device=self.dev)
         e, ep = self._eps(eps)
-        _lib.check(self.lib.tbnn_trajectory(self.h, _ptr(theta), _ptr(hyper), _ptr(momentum), ep, int(L),
-                                            _ptr(th), _ptr(p), _ptr(lp), _ptr(g), _stream()))
+        self._call(self.lib.tbnn_trajectory, (self.h, _ptr(theta), _ptr(hyper), _ptr(momentum), ep, int(L),
+                                            _ptr(th), _ptr(p), _ptr(lp), _ptr(g), self._st()))
         return th, p, lp, g
 
     def hmc_step(self, theta, hyper, seed, counter, eps, L, momentum=None, u=None, stats=None):
@@ -136,21 +146,21 @@ class Engine(object):
         if stats is None:
             stats = torch.empty(self.chains, 4, dtype=self.dtype, device=self.dev)
         e, ep = self._eps(eps)
-        _lib.check(self.lib.tbnn_hmc_step(self.h, _ptr(theta), _ptr(hyper), int(seed), int(counter), ep,
-                                          int(L), _ptr(momentum), _ptr(u), _ptr(stats), _stream()))
+        self._call(self.lib.tbnn_hmc_step, (self.h, _ptr(theta), _ptr(hyper), int(seed), int(counter), ep,
+                                          int(L), _ptr(momentum), _ptr(u), _ptr(stats), self._st()))
         return stats
 
     def draw_momentum(self, seed, counter):
         p = torch.empty(self.chains, self.P, dtype=self.dtype, device=self.dev)
         ke = torch.empty(self.chains, dtype=self.dtype, device=self.dev)
-        _lib.check(self.lib.tbnn_draw_momentum(self.h, int(seed), int(counter), _ptr(p), _ptr(ke), _stream()))
+        self._call(self.lib.tbnn_draw_momentum, (self.h, int(seed), int(counter), _ptr(p), _ptr(ke), self._st()))
         return p, ke
 
     def time_sweep(self, theta, iters=20):
         """(avg_ms, min_ms) of the row-sweep kernel, CUDA events on the launching stream."""
         theta = self.tensor(theta, (self.chains, self.P))
         a, m = C.c_float(), C.c_float()
-        _lib.check(self.lib.tbnn_time_sweep(self.h, _ptr(theta), int(iters), C.byref(a), C.byref(m), _stream()))
+        self._call(self.lib.tbnn_time_sweep, (self.h, _ptr(theta), int(iters), C.byref(a), C.byref(m), self._st()))
         return float(a.value), float(m.value)
 
     def hyper_step(self, theta, hyper, seed, counter, hyperL, epoch, burnin, hyper_step0, da_state,
@@ -165,10 +175,10 @@ class Engine(object):
             u = self.tensor(u, (self.chains,))
         if stats is None:
             stats = torch.empty(self.chains, 2, dtype=self.dtype, device=self.dev)
-        _lib.check(self.lib.tbnn_hyper_step(self.h, _ptr(theta), _ptr(hyper), int(seed), int(counter),
+        self._call(self.lib.tbnn_hyper_step, (self.h, _ptr(theta), _ptr(hyper), int(seed), int(counter),
                                             int(hyperL), float(epoch), float(burnin), float(hyper_step0),
                                             _ptr(da_state), _ptr(momentum), _ptr(u), _ptr(stats),
-                                            _stream()))
+                                            self._st()))
         return stats
 
     # ------------------------------------------------------------------ predictor
@@ -182,14 +192,14 @@ class Engine(object):
         n_out = [l for l in self.arch if l[0] in _lib.DENSE][-1][2]
         out = torch.empty(S, n_out, M, dtype=self.dtype, device=self.dev) if want_out else None
         mom = torch.zeros(3, n_out, M, dtype=self.dtype, device=self.dev) if want_moments else None
-        _lib.check(self.lib.tbnn_predict(self.h, _ptr(samples), S, _ptr(X), M, _ptr(out), _ptr(mom),
-                                         _stream()))
+        self._call(self.lib.tbnn_predict, (self.h, _ptr(samples), S, _ptr(X), M, _ptr(out), _ptr(mom),
+                                         self._st()))
         return out, mom
 
     # ------------------------------------------------------------------ multi-GPU (row sharding)
     def comm_init(self, unique_id, rank, world):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
-        _lib.check(self.lib.tbnn_comm_init(self.h, C.cast(buf, C.c_void_p), int(rank), int(world)))
+        self._call(self.lib.tbnn_comm_init, (self.h, C.cast(buf, C.c_void_p), int(rank), int(world)))
 
     @staticmethod
     def comm_unique_id():

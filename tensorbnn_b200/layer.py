@@ -102,7 +102,8 @@ class _DenseBase(Layer):
         self.tdtype = to_torch_dtype(dtype)
         self.seed = seed
         self.name = self._kind
-        self.hypers = torch.tensor([[v] for v in self._init_hypers], dtype=self.tdtype)   # [4,1]
+        # tf.cast([[...]], dtype) of python floats passes through float32 (layer.py:156-158; quirk Q14)
+        self.hypers = torch.tensor([[v] for v in self._init_hypers], dtype=torch.float32).to(self.tdtype)   # [4,1]
         if weights is None:
             self.parameters = self.sample()
         else:

@@ -28,7 +28,10 @@ class Likelihood(object):
         return net._log_likelihood(argv[0] if len(argv) else None, kwargs.get("hyperStates"), self)
 
     def calcultateLogProb(self, *argv, **kwargs):
-        raise NotImplementedError("predictor.reweight is outside the accelerated hot path (SURVEY 8f, row f3)")
+        """(sic)  The per-sample likelihood terms of predictor.trainProbs / reweight are evaluated on the device by
+        predictor._neg_log_weights; this host method exists for interface compatibility only."""
+        raise NotImplementedError("use predictor.trainProbs / predictor.reweight: the per-sample likelihood is "
+                                  "evaluated on the device there")
 
     def display(self, hypers):
         pass

@@ -1,7 +1,6 @@
-"""Display metrics with the reference's interface (tensorBNN/metrics.py).  They are off the
-sampling hot path (out of scope as kernels): the two forward passes they
-consume come from the CUDA predict kernel, the few reductions below are torch ops on the
-device tensors."""
+"""Display metrics with the reference's interface (tensorBNN/metrics.py).  The two forward passes they consume
+come from the CUDA predict kernel; the reductions are torch ops on those device tensors and their results STAY on
+the device (calculate() never synchronises) -- only display(), which prints, reads them back."""
 import torch
 
 
@@ -39,12 +38,12 @@ class SquaredError(Metric):
         if self.scaleExp:
             pt, rt, rv = torch.exp(pt), torch.exp(rt), torch.exp(rv)
         rt, rv = rt.reshape(pt.shape), rv.reshape(pv.shape)
-        self.squaredErrorTrain = float(torch.mean((pt - rt) ** 2))
-        self.squaredErrorValidate = float(torch.mean((pv - rv) ** 2))
+        self.squaredErrorTrain = torch.mean((pt - rt) ** 2)
+        self.squaredErrorValidate = torch.mean((pv - rv) ** 2)
 
     def display(self):
-        print("training squared error{: 9.5f}".format(self.squaredErrorTrain),
-              "validation squared error{: 9.5f}".format(self.squaredErrorValidate))
+        print("training squared error{: 9.5f}".format(float(self.squaredErrorTrain)),
+              "validation squared error{: 9.5f}".format(float(self.squaredErrorValidate)))
 
 
 class PercentError(Metric):
@@ -52,12 +51,12 @@ class PercentError(Metric):
 
     def calculate(self, predictionsTrain, predictionsValidate, realTrain, realValidate):
         pt, pv, rt, rv = self._prep(predictionsTrain, predictionsValidate, realTrain, realValidate)
-        self.percentErrorTrain = float(torch.mean(torch.abs((pt - rt) / rt) * 100))
-        self.percentErrorValidate = float(torch.mean(torch.abs((pv - rv) / rv) * 100))
+        self.percentErrorTrain = torch.mean(torch.abs((pt - rt) / rt) * 100)
+        self.percentErrorValidate = torch.mean(torch.abs((pv - rv) / rv) * 100)
 
     def display(self):
-        print("training percent error{: 7.3f}".format(self.percentErrorTrain),
-              "validation percent error{: 7.3f}".format(self.percentErrorValidate))
+        print("training percent error{: 7.3f}".format(float(self.percentErrorTrain)),
+              "validation percent error{: 7.3f}".format(float(self.percentErrorValidate)))
 
 
 class Accuracy(Metric):
@@ -65,9 +64,9 @@ class Accuracy(Metric):
 
     def calculate(self, predictionsTrain, predictionsValidate, realTrain, realValidate):
         pt, pv, rt, rv = self._prep(predictionsTrain, predictionsValidate, realTrain, realValidate)
-        self.accuracyTrain = float(1 - torch.mean(torch.abs(rt - torch.round(pt))))
-        self.accuracyValidate = float(1 - torch.mean(torch.abs(rv - torch.round(pv))))
+        self.accuracyTrain = 1 - torch.mean(torch.abs(rt - torch.round(pt)))
+        self.accuracyValidate = 1 - torch.mean(torch.abs(rv - torch.round(pv)))
 
     def display(self):
-        print("training accuracy{: 9.5f}".format(self.accuracyTrain),
-              "validation accuracy{: 9.5f}".format(self.accuracyValidate))
+        print("training accuracy{: 9.5f}".format(float(self.accuracyTrain)),
+              "validation accuracy{: 9.5f}".format(float(self.accuracyValidate)))

@@ -44,6 +44,8 @@ class network(object):
         self.metricList = []
         self.likelihood = None
         self._engine = None
+        self._engine_key = None
+        self._rng_calls = 0     # Philox call counter, persistent across train() calls (a second call draws fresh numbers)
         self._pred_engine = None
         self._theta = None      # [C, P] device
         self._hyper = None      # [C, H] device
@@ -75,7 +77,8 @@ class network(object):
                                   leapfogMin, leapFrogMax, leapfrogIncrement, averagingSteps,
                                   burnin / averagingSteps, a=a, delta=delta, cores=cores, strikes=strikes,
                                   randomSteps=randomSteps, device=self.device)
-        self.step_size = float(stepSizeStart)
+        # tf.cast(stepSizeStart, dtype): a python float passes through float32 (network.py:237; quirk Q14)
+        self.step_size = float(np.float32(stepSizeStart))
         self.leapfrog = int(leapfrogStart)
         self.cores = cores
         self.burnin = burnin
@@ -105,7 +108,7 @@ class network(object):
     def _bind_state_views(self):
         """network.states / hyperStates become views into the flat device state of chain 0
         (or [C, ...] views when chains > 1), so user reads always see the current sample."""
-        shapes = [tuple(s.shape) for s in self.states]
+        shapes = self._state_shapes
         off, views = 0, []
         for sh in shapes:
             n = int(np.prod(sh))
@@ -120,24 +123,48 @@ class network(object):
         self.hyperStates = hv
 
     def _ensure_device_state(self, likelihood):
-        if self._engine is not None:
+        """Builds (or rebuilds) the engine and the flat device state.  The cache is keyed on the architecture AND the
+        likelihood: calculateProbs() before train() builds an engine without the likelihood's hyper parameter, and a
+        later train(GaussianLikelihood(...)) must not keep sampling with that stale engine."""
+        key = (repr(self.arch_spec()), repr(self._lik_spec(likelihood)))
+        if self._engine is not None and self._engine_key == key:
             return
+        if self._engine is not None:
+            # keep the current sample: the views die with the old flat state
+            self.states = [s.detach().clone() for s in self.states]
+            self.hyperStates = [h.detach().clone().reshape(-1) if self.chains == 1 else h.detach().clone()
+                                for h in self.hyperStates]
         self._engine = self._make_engine(likelihood)
+        self._engine_key = key
         eng = self._engine
-        flat = self._flat_states()
-        if flat.numel() != eng.P:
-            raise ValueError("states hold %d values but the network has %d parameters" % (flat.numel(), eng.P))
-        hy = torch.cat([h.reshape(-1).to(self.tdtype).cpu() for h in self.hyperStates])
-        if hy.numel() != eng.H:
-            raise ValueError("hyperStates hold %d values but the network has %d hyper parameters"
-                             % (hy.numel(), eng.H))
-        self._theta = flat.reshape(1, -1).repeat(self.chains, 1).to(eng.dev).contiguous()
-        if self.chains > 1:
+        C = self.chains
+        bound = self._theta is not None            # states already are [C, ...] views / copies of a flat state
+        self._state_shapes = [tuple(s.shape[1:]) if (bound and C > 1) else tuple(s.shape) for s in self.states]
+
+        def flat(tensors, width):
+            parts = []
+            for t in tensors:
+                t = t.to(self.tdtype).cpu()
+                per_chain = bound and C > 1 and t.dim() >= 2 and t.shape[0] == C
+                parts.append(t.reshape(C, -1) if per_chain else t.reshape(1, -1))
+            rows = max([q.shape[0] for q in parts] + [1])
+            parts = [q if q.shape[0] == rows else q.repeat(rows, 1) for q in parts]
+            out = torch.cat(parts, dim=1) if parts else torch.zeros(1, 0, dtype=self.tdtype)
+            if out.shape[1] != width:
+                raise ValueError("the network state holds %d values but the engine expects %d" % (out.shape[1], width))
+            return out
+
+        th = flat(self.states, eng.P)
+        hy = flat(self.hyperStates, eng.H)
+        if th.shape[0] == 1 and C > 1:
+            th = th.repeat(C, 1)
             # independent chains start from jittered copies of the given state
             g = torch.Generator().manual_seed(self.seed)
-            jit = 0.01 * torch.randn(self.chains - 1, eng.P, generator=g, dtype=torch.float64)
-            self._theta[1:] += jit.to(self._theta)
-        self._hyper = hy.reshape(1, -1).repeat(self.chains, 1).to(eng.dev).contiguous()
+            th[1:] += (0.01 * torch.randn(C - 1, eng.P, generator=g, dtype=torch.float64)).to(th)
+        if hy.shape[0] == 1 and C > 1:
+            hy = hy.repeat(C, 1)
+        self._theta = th.to(eng.dev).contiguous()
+        self._hyper = hy.to(eng.dev).contiguous()
         self._bind_state_views()
 
     # ------------------------------------------------------------------ prediction / probabilities
@@ -180,13 +207,20 @@ class network(object):
 
     def calculateProbs(self, *argv, sd=None):
         """Log posterior of the given (or current) states under the current hypers
-        (the closure of reference network.py:370-392)."""
-        states = self.states if len(argv) == 0 else (argv[0] if len(argv) != len(self.states) else argv)
+        (the closure of reference network.py:370-392).  Needs the likelihood: call train() first or set
+        ``network.likelihood``."""
+        if self.likelihood is None:
+            raise RuntimeError("calculateProbs needs a likelihood: set network.likelihood or call train() first")
         self._ensure_device_state(self.likelihood)
         eng = self._engine
-        th = torch.cat([as_tensor(t, self.tdtype).reshape(-1).to(eng.dev) for t in states]).reshape(1, -1)
-        lp, _, _ = eng.logp_grad(th.repeat(eng.chains, 1) if self.chains > 1 else th, self._hyper)
-        return lp[0]
+        if len(argv) == 0:
+            th = self._theta
+        else:
+            states = argv[0] if len(argv) != len(self.states) else argv
+            th = torch.cat([as_tensor(t, self.tdtype).reshape(-1).to(eng.dev) for t in states]).reshape(1, -1)
+            th = th.repeat(eng.chains, 1) if self.chains > 1 else th
+        lp, _, _ = eng.logp_grad(th, self._hyper)
+        return lp[0] if self.chains == 1 else lp
 
     def metrics(self, trainPredict, trainReal, validatePredict, validateReal):
         for metric in self.metricList:
@@ -224,7 +258,8 @@ class network(object):
         self.adjustHypers = adjustHypers
         if not self._lik_appended:             # calling train twice must not duplicate them (Q12)
             for val in likelihood.hypers:
-                self.hyperStates.append(as_tensor(val, self.tdtype).reshape(-1))
+                # tf.cast(val, dtype) of python floats passes through float32 (network.py:542-543; quirk Q14)
+                self.hyperStates.append(torch.tensor(val, dtype=torch.float32).to(self.tdtype).reshape(-1))
             self._lik_appended = True
         self._ensure_device_state(likelihood)
         eng = self._engine
@@ -242,34 +277,63 @@ class network(object):
                 with open(os.path.join(d, "architecture.txt"), "wb") as f:
                     for layer in self.layers:
                         f.write((layer.name + "\n").encode("utf-8"))
+                # constants of stateless layers that architecture.txt cannot carry (Leaky_relu's slope is not a
+                # sampled state here, Q6): side-car read back by this package's predictor
+                consts = [(i, layer.alpha) for i, layer in enumerate(self.layers) if layer.name == "leakyrelu"]
+                if consts:
+                    with open(os.path.join(d, "layer_params.txt"), "w") as f:
+                        for i, alpha in consts:
+                            f.write("%d alpha %r\n" % (i, float(alpha)))
 
         da_state = torch.tensor([[self.h, self.logEpsilonBar, self.hyper_step_size]], dtype=self.tdtype)
         da_state = da_state.repeat(C, 1).to(eng.dev).contiguous()
         stats = torch.zeros(C, 4, dtype=self.tdtype, device=eng.dev)
         hstats = torch.zeros(C, 2, dtype=self.tdtype, device=eng.dev)
-        host = torch.zeros(C, 9, dtype=self.tdtype).pin_memory()
+        # The host reads nine scalars per chain and epoch (accept probabilities, squared jump distance for the adapter,
+        # dual-averaging state) -- but only when it needs them: the adapter can change (step size, L) only on its
+        # decision epochs (every `averagingSteps`-th call), so the epochs in between are queued on the stream without
+        # a synchronisation and their rows are consumed together (pinned ring, asynchronous copies).
+        ring = torch.zeros(max(2, int(self.adapt.m) + 1), C, 9, dtype=self.tdtype).pin_memory()
+        pending = []
         self.mainAccept = 0.0
         self.hyperAccept = 0.0
+
+        def consume():
+            if not pending:
+                return
+            torch.cuda.current_stream(eng.dev).synchronize()
+            for slot in pending:
+                row = ring[slot]
+                self.mainAccept = float(row[:, 1].mean())
+                self.hyperAccept = float(row[:, 5].mean())
+                self.h, self.logEpsilonBar = float(row[0, 6]), float(row[0, 7])
+                self.hyper_step_size = float(row[0, 8])
+                step, leap = self.adapt.update(sjd=float(row[:, 3].mean()))
+                self.step_size = float(step)
+                self.leapfrog = int(leap)
+            del pending[:]
+
         iter_ = 0
         startTime = time.time()
         while iter_ < epochs:
-            eng.hmc_step(self._theta, self._hyper, self.seed, iter_, self.step_size, self.leapfrog, stats=stats)
+            eng.hmc_step(self._theta, self._hyper, self.seed, self._rng_calls, self.step_size, self.leapfrog, stats=stats)
             if adjustHypers and eng.H > 0:
-                eng.hyper_step(self._theta, self._hyper, self.seed, iter_, self.hyperLeapfrog, float(iter_),
+                eng.hyper_step(self._theta, self._hyper, self.seed, self._rng_calls, self.hyperLeapfrog, float(iter_),
                                float(self.burnin), self.hyperStepSize0, da_state, stats=hstats)
-            host[:, 0:4].copy_(stats, non_blocking=True)
-            host[:, 4:6].copy_(hstats, non_blocking=True)
-            host[:, 6:9].copy_(da_state, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            self.mainAccept = float(host[:, 1].mean())
-            self.hyperAccept = float(host[:, 5].mean())
-            self.h, self.logEpsilonBar = float(host[0, 6]), float(host[0, 7])
-            self.hyper_step_size = float(host[0, 8])
-            sjd = float(host[:, 3].mean())
+            self._rng_calls += 1
+            slot = len(pending)
+            ring[slot, :, 0:4].copy_(stats, non_blocking=True)
+            ring[slot, :, 4:6].copy_(hstats, non_blocking=True)
+            ring[slot, :, 6:9].copy_(da_state, non_blocking=True)
+            pending.append(slot)
             iter_ += 1
             self.iteration = iter_
+            display = verbose and iter_ % displaySkip == 0
+            saving = bool(folderName) and iter_ > startSampling
+            if display or saving or len(pending) >= ring.shape[0] or self.adapt.calls_until_decision() < len(pending):
+                consume()
 
-            if verbose and iter_ % displaySkip == 0:
+            if display:
                 print()
                 print("iter:{:>2}".format(iter_))
                 print("step size", self.step_size)
@@ -277,11 +341,10 @@ class network(object):
                 print("leapfrog", self.leapfrog)
                 print("Main acceptance", self.mainAccept)
                 print("Hyper acceptance", self.hyperAccept)
-                self.metrics(self.predict(train=True), self.trainY.to(eng.dev),
-                             self.predict(train=False), self.validateY.to(eng.dev))
-            step, leap = self.adapt.update(sjd=sjd)
-            self.step_size = float(step)
-            self.leapfrog = int(leap)
+                ptrain, pval = self.predict(train=True), self.predict(train=False)
+                if C > 1:                              # metrics are displayed for the first chain
+                    ptrain, pval = ptrain[0], pval[0]
+                self.metrics(ptrain, self.trainY.to(eng.dev), pval, self.validateY.to(eng.dev))
 
             # file rollover + summary (reference network.py:609-646, lagging summary of Q9 reproduced)
             indexShift = iter_ - startSampling - 1
@@ -321,6 +384,7 @@ class network(object):
                 likelihood.display(self.hyperStates)
                 print("Time elapsed:", time.time() - startTime)
                 startTime = time.time()
+        consume()
         for fl in files:
             for fh in fl:
                 fh.close()

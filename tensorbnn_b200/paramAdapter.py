@@ -89,6 +89,15 @@ class paramAdapter(object):
             val += float(torch.sum(d * d)) / float(F(F(L) ** F(0.5)))
         return F(val)
 
+    def calls_until_decision(self):
+        """How many update() calls can be made before the one that may change (step size, L): that is the call made
+        while ``i % m == 0 and i > 0`` (reference :231).  0 = the very next call may decide."""
+        i, m = int(self.i), int(self.m)
+        k = 0
+        while not ((i + k) % m == 0 and (i + k) > 0):
+            k += 1
+        return k
+
     def update(self, state=None, sjd=None):
         """One adapter step (reference :199-292).  Returns (float32 step size, int32 leapfrog)."""
         if self.i < self.k - 2 and self.strikes == self.maxStrikes:

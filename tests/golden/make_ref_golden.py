@@ -418,6 +418,8 @@ def run_case():
     Xt = rng.normal(size=(5, 2)).astype(np.float32)
     outs = pred.predict(Xt, n=1)
     outs2 = pred.predict(Xt, n=2)
+    acf = pred.autocorrelation(Xt, 4)                   # predictor.py:275-292 over the emcee stand-in
+    acl = pred.autoCorrelationLength(Xt, 4)             # :294-312
     return {"source": "reference network.train writer + predictor reader run unmodified over oracle/tfshim",
             "arch": [list(l) for l in arch], "lik": list(lik), "files": files,
             "line_counts": {f: sum(1 for _ in open(os.path.join(dst, f))) for f in files},
@@ -425,7 +427,8 @@ def run_case():
             "schedule": {"epochs": 15, "burnin": 2, "samplingStep": 2, "networksPerFile": 3},
             "numNetworks": int(pred.numNetworks), "matrix_shapes": [list(m.shape) for m in pred.matrices],
             "hypers": [r(h) for h in pred.hypers], "Xtest": r(Xt), "predict_n1": [r(o) for o in outs],
-            "predict_n2": [r(o) for o in outs2], "final_states": [r(s) for s in net.states],
+            "predict_n2": [r(o) for o in outs2],
+            "autocorrelation_nmax4": r(acf), "autocorrelation_length": float(acl), "final_states": [r(s) for s in net.states],
             "final_hypers": r(np.concatenate([np.asarray(r(h)) for h in net.hyperStates]))}
 
 

@@ -234,7 +234,8 @@ def test_network_bookkeeping_matches_reference_layout():
     assert [float(h) for h in net.hyperStates[4:6]] == pytest.approx([0.0, 0.3])
     assert net.arch_spec() == [("dense", 1, 4), ("squareprelu", 4), ("denseGaussian", 4, 1), ("relu",)]
     net.setupMCMC(0.001, 0.0005, 0.002, 100, 500, 100, 2000, 1, 1e-5, 30, 50, 2, 2)   # docs positional call
-    assert net.step_size == 0.001 and net.leapfrog == 500 and net.hyperLeapfrog == 30 and net.burnin == 50
+    # tf.cast(stepSizeStart, dtype) passes the python float through float32 (network.py:237, Q14)
+    assert net.step_size == float(np.float32(0.001)) and net.leapfrog == 500 and net.hyperLeapfrog == 30 and net.burnin == 50
     assert net.adapt.eNumber == 100 and net.adapt.lNumber == 1901 and net.adapt.k == 25 and net.adapt.m == 2
     assert abs(net.mu - math.log(100 * 1e-5)) < 1e-12
 
