@@ -501,6 +501,11 @@ def main():
             "algorithmic_bytes_per_launch": abytes, "algorithmic_flops_per_launch": C * flops_per_chain_step(cfg),
             "hbm_gbs": hbm_gbs, "hbm_frac": hbm_gbs / peaks["hbm_gbs"], "fp32_equivalent_tflops": tflops,
             "ffma_frac": tflops / ffma_peak}
+    if rows_sharded:
+        ar_avg, ar_min = eng.time_allreduce(iters=30)
+        roof["allreduce"] = {"ms": ar_avg, "ms_min": ar_min, "values": int(C * (eng.P + 4)),
+                             "share_of_step": ar_avg * (L + 1) * args.steps / dev_ms,
+                             "what": "local reduction of the CTA partials + ncclAllReduce per gradient evaluation (CUDA events)"}
     if info["kernel"] == "k_train_umma":
         roof.update({"bound": "tensor", "achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak,
                      "note": "useful fp32-equivalent flops N(6F - 2 d0 d1) per chain-step (SURVEY 8d); peak = measured sustained "

@@ -152,6 +152,11 @@ int tbnn_draw_momentum(tbnn_handle* h, uint64_t seed, uint64_t counter, void* mo
 int tbnn_time_sweep(tbnn_handle* h, const void* theta, int iters, float* avg_ms, float* min_ms,
                     void* stream);
 
+/* Measurement hook for the row-sharded path (after tbnn_comm_init and one gradient evaluation): times the
+ * per-gradient-evaluation exchange -- local reduction of the CTA partials + ncclAllReduce of C*(Ppad+4) values -- `iters`
+ * times with CUDA events on `stream`; average / minimum in milliseconds.  Collective: every rank must call it. */
+int tbnn_time_allreduce(tbnn_handle* h, int iters, float* avg_ms, float* min_ms, void* stream);
+
 /* One HMC transition of the hyper chain + the hand-rolled dual averaging of
  * network.py:442-471 (constants :241-248).  hyper[C][H] updated in place.
  * da_state[C][3] (dtype) = {h, logEpsilonBar, hyper_step_size}, updated in place.

@@ -24,7 +24,7 @@ FLAG_UMMA_SWEEP = 8  # tbnn_desc.flags: wide-first-layer sweep on tcgen05 (k_swe
 EXPORTS = ["tbnn_last_error", "tbnn_version", "tbnn_create", "tbnn_destroy", "tbnn_num_params",
            "tbnn_num_hypers", "tbnn_launch_count", "tbnn_sweep_info", "tbnn_wide_profile", "tbnn_predict_info", "tbnn_set_data", "tbnn_set_data_host",
            "tbnn_logp_grad", "tbnn_hyper_logp_grad", "tbnn_trajectory", "tbnn_hmc_step",
-           "tbnn_draw_momentum", "tbnn_time_sweep", "tbnn_hyper_step", "tbnn_adapter_ucb", "tbnn_predict", "tbnn_comm_unique_id",
+           "tbnn_draw_momentum", "tbnn_time_sweep", "tbnn_time_allreduce", "tbnn_hyper_step", "tbnn_adapter_ucb", "tbnn_predict", "tbnn_comm_unique_id",
            "tbnn_comm_init"]
 
 
@@ -74,6 +74,7 @@ def load():
     lib.tbnn_hmc_step.argtypes = [vp, vp, vp, u64, u64, pd, i32, vp, vp, vp, vp]
     lib.tbnn_draw_momentum.argtypes = [vp, u64, u64, vp, vp, vp]
     lib.tbnn_time_sweep.argtypes = [vp, vp, i32, pf, pf, vp]
+    lib.tbnn_time_allreduce.argtypes = [vp, i32, pf, pf, vp]
     lib.tbnn_hyper_step.argtypes = [vp, vp, vp, u64, u64, i32, dbl, dbl, dbl, vp, vp, vp, vp, vp]
     lib.tbnn_adapter_ucb.argtypes = [i32, pf, i32, pf, i32, pf, i32, pf, pf, flt, flt, flt, flt, flt, flt,
                                      flt, pf, pf, pf]

@@ -764,6 +764,39 @@ extern "C" int tbnn_time_sweep(tbnn_handle* h, const void* theta, int iters, flo
                               : time_sweep_impl<double>(h, theta, iters, avg_ms, min_ms, st);
 }
 
+// Measurement hook for the row-sharded path: the per-gradient-evaluation exchange (k_reduce_partials + ncclAllReduce of
+// C * (Ppad + 4) values), `iters` times, each bracketed by CUDA events on `stream`.
+extern "C" int tbnn_time_allreduce(tbnn_handle* h, int iters, float* avg_ms, float* min_ms, void* stream) {
+  CK(check_ready(h));
+  if (!h->comm) return fail("tbnn_time_allreduce needs a communicator (tbnn_comm_init)");
+  if (iters < 1 || !avg_ms || !min_ms) return fail("bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double tot = 0.0;
+  float mn = 1e30f;
+  for (int i = 0; i < iters + 2; ++i) {
+    CU(cudaEventRecord(e0, st));
+    if (h->dtype == TBNN_F32)
+      Launch<float>::reduce_partials(h->mp, h->C, h->S, (const float*)h->partial, h->stat_part, (float*)h->gsum, st);
+    else
+      Launch<double>::reduce_partials(h->mp, h->C, h->S, (const double*)h->partial, h->stat_part, (double*)h->gsum, st);
+    NC(g_nccl.AllReduce(h->gsum, h->gsum, (size_t)h->C * (h->mp.Ppad + 4), h->dtype == TBNN_F32 ? 7 : 8, 0, h->comm, st));
+    CU(cudaEventRecord(e1, st));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (i >= 2) { tot += ms; mn = std::min(mn, ms); }
+    h->launches += 1;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *avg_ms = (float)(tot / iters);
+  *min_ms = mn;
+  return 0;
+}
+
 // Developer aid: phase clocks (clock64 of CTA 0) of one wide-sweep launch; clocks[0] = number of marks.
 extern "C" int tbnn_wide_profile(tbnn_handle* h, const void* theta, long long* clocks_host64, void* stream) {
   CK(check_ready(h));

@@ -163,6 +163,12 @@ class Engine(object):
         self._call(self.lib.tbnn_time_sweep, (self.h, _ptr(theta), int(iters), C.byref(a), C.byref(m), self._st()))
         return float(a.value), float(m.value)
 
+    def time_allreduce(self, iters=20):
+        """(avg_ms, min_ms) of the per-gradient-evaluation exchange of the row-sharded path (collective call)."""
+        a, m = C.c_float(), C.c_float()
+        self._call(self.lib.tbnn_time_allreduce, (self.h, int(iters), C.byref(a), C.byref(m), self._st()))
+        return float(a.value), float(m.value)
+
     def hyper_step(self, theta, hyper, seed, counter, hyperL, epoch, burnin, hyper_step0, da_state,
                    momentum=None, u=None, stats=None):
         """hyper [C,H] and da_state [C,3] = (h, logEpsilonBar, step) are updated IN PLACE."""
