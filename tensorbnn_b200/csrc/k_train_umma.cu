@@ -37,7 +37,9 @@ namespace tbnn {
 
 constexpr int TU_THREADS = 320;          // warps 0-7 row workers, warp 8 MMA issuer (+ TMEM alloc), warp 9 TMA producer
 constexpr int TU_MMA_WARP = 8, TU_TMA_WARP = 9;
-constexpr int TU_NS = 3;                       // ring stages
+constexpr int TU_NS_MAX = 4;                   // ring stages: 4 for the 64-wide network (all four chunks of a weight-gradient GEMM
+                                               // in flight at once), 3 for the 128-wide one (shared memory)
+__host__ __device__ constexpr int tu_ns(int hw) { return hw == 64 ? 4 : 3; }
 constexpr int TU_CGA = 128 * 16 + 16;          // column-group stride (bytes) of a 128-row operand chunk
 constexpr int TU_HALFA = 8 * TU_CGA;           // bytes of its hi (or lo) half
 constexpr int TU_ASTAGE = 2 * TU_HALFA;
@@ -167,10 +169,33 @@ __device__ __forceinline__ void put_t(uint32_t stage, int half, int cgs, int n, 
   sts32(a + half, l);
 }
 
+// Optional clock64 timeline of CTA 0 (build with -DTBNN_TU_PROFILE; read with tbnn_tu_profile): (tag, clock) pairs of
+// row-worker warp 0 (role 0) and of the MMA issuer (role 1).  tag = role << 28 | k << 20 | ti << 16 | phase.
+#ifdef TBNN_TU_PROFILE
+__device__ long long g_tu_prof[2][2][4096];
+__device__ int g_tu_prof_n[2];
+#define TU_MARK(role, k, ti, phase)                                                                         \
+  do {                                                                                                      \
+    if (blockIdx.x == 0 && g_tu_prof_n[role] < 4096) {                                                      \
+      const int i_ = g_tu_prof_n[role]++;                                                                   \
+      g_tu_prof[role][0][i_] = ((long long)(role) << 28) | ((long long)(k) << 20) | ((long long)(ti) << 16) | (phase); \
+      g_tu_prof[role][1][i_] = clock64();                                                                   \
+    }                                                                                                       \
+  } while (0)
+#else
+#define TU_MARK(role, k, ti, phase) do { } while (0)
+#endif
+
 struct TuBars {
-  uint64_t fullA[TU_NS], emptyA[TU_NS], fullB[TU_NS], emptyB[TU_NS], accfull[2], accfree[2];
+  uint64_t fullA[TU_NS_MAX], emptyA[TU_NS_MAX], fullB[TU_NS_MAX], emptyB[TU_NS_MAX], accfull[4], accfree[4];   // acc*: [tile slot][F/B, W]
 };
 
+// Tiles in flight per CTA.  A tile is a serial chain (F_0 -> epilogue -> F_1 -> ... -> B_1 -> epilogue -> W_0); with two
+// tiles in flight the row workers run one tile's epilogue while the tensor core runs the other tile's GEMM.  Tensor
+// memory holds two tiles' accumulators only for the 64-wide network.
+template <int HW> struct TuTiles { static constexpr int value = HW == 64 ? 2 : 1; };
+
+// 168 registers per thread: register allocation rounds the 10 warps up to 12 (a launch with 200 is refused)
 template <int HW, int ACTK>
 __global__ void __launch_bounds__(TU_THREADS, 1)
 k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ TrainUmmaPlan tp, int C, int S,
@@ -179,6 +204,8 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
              double* __restrict__ stat_part, float* __restrict__ scratch) {
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ uint32_t tmem_slot;
+  constexpr int NT = TuTiles<HW>::value;        // tiles in flight
+  constexpr int TU_NS = tu_ns(HW);              // ring stages
   constexpr int nH = HW / 32;                   // chunks of a hidden-width contraction
   constexpr int HH = HW / 2;                    // columns per row worker (two threads share a row)
   constexpr int nHH = HH / 32;                  // chunks per column group
@@ -200,7 +227,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       mbar_init(&bars->fullB[i], 2);
       mbar_init(&bars->emptyB[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->accfull[i], 1);
       mbar_init(&bars->accfree[i], 8);
     }
@@ -211,9 +238,16 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tbase = tmem_slot;
-  // tensor memory columns: F / B accumulator [0,128) (F GEMMs: the hi*hi products), the small products of the F GEMMs
-  // [128,256) -- two short chains instead of one long one, the accumulator rounds toward zero -- and W GEMMs [256,400)
-  constexpr uint32_t COL_BIG = 0u, COL_SMALL = 128u, COL_W = 256u;
+  // Tensor-memory columns of tile slot ti.  F / B accumulator (F GEMMs: the hi*hi products), the small products of the
+  // F GEMMs -- two short accumulation chains instead of one long one, the accumulator rounds toward zero -- and the W
+  // GEMMs.  HW = 128: [0,128) [128,256) [256,400); HW = 64, two slots: [128 ti, +64) [128 ti + 64, +64) [256 + 80 ti, +80).
+  auto col_big = [](int ti) -> uint32_t { return (uint32_t)(128 * ti); };
+  auto col_small = [](int ti) -> uint32_t { return (uint32_t)(NT == 2 ? 128 * ti + 64 : 128); };
+  auto col_w = [](int ti) -> uint32_t { return (uint32_t)(256 + (NT == 2 ? 80 * ti : 0)); };
+  // Segments of a tile, in order (k = 0 .. 2G): 0: X -> F_0 operands | 1..G-1: epilogue of F_{k-1} -> F_k operands |
+  // G: epilogue of F_{G-1}, last block, likelihood, dZ_{G-1} -> B_{G-1}, W_{G-1} operands | G+j: epilogue of B_{G-j} ->
+  // B_{G-1-j}, W_{G-1-j} operands | 2G: drain W_0.  The tiles in flight alternate segment by segment; every role walks
+  // through (tile group, segment, tile slot) in the same order, so the operand rings see one fixed chunk sequence.
 
   if (warp == TU_TMA_WARP) {
     // ================================================================ TMA producer
@@ -240,40 +274,49 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         const int c = item / S, s = item - c * S;
         const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
         const unsigned char* img = wimg + (size_t)c * tp.wimg_chain;
-        for (long long t = t0; t < t1; ++t) {
-          for (int l = 0; l < G; ++l) {
-            const int nch = l == 0 ? tp.nK0 : nH;
-            for (int ch = 0; ch < nch; ++ch) load(img + tp.fimg[l] + (size_t)ch * cbytes);
+        for (long long tb = t0; tb < t1; tb += NT) {
+          const int ntl = NT == 1 ? 1 : (int)((t1 - tb) < NT ? (t1 - tb) : NT);
+          for (int k = 0; k < 2 * G; ++k) {
+            for (int ti = 0; ti < ntl; ++ti) {
+              if (k < G) {                                   // F_k
+                const int nch = k == 0 ? tp.nK0 : nH;
+                for (int ch = 0; ch < nch; ++ch) load(img + tp.fimg[k] + (size_t)ch * cbytes);
+              } else {                                       // B_l (l >= 1), W_l
+                const int l = 2 * G - 1 - k;
+                if (l >= 1)
+                  for (int ch = 0; ch < nH; ++ch) load(img + tp.bimg[l] + (size_t)ch * cbytes);
+                skip_w();
+              }
+            }
           }
-          for (int l = G - 1; l >= 1; --l) {
-            for (int ch = 0; ch < nH; ++ch) load(img + tp.bimg[l] + (size_t)ch * cbytes);
-            skip_w();    // W_l: both operands come from the row workers
-          }
-          skip_w();      // W_0
         }
       }
     }
   } else if (warp == TU_MMA_WARP) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      uint32_t cc = 0, accuse[2] = {0u, 0u};
+      uint32_t cc = 0, accuse[4] = {0u, 0u, 0u, 0u};
       const uint32_t idF = umma::idesc_tf32(128, HW, false, false);
       const uint32_t idWh = umma::idesc_tf32(128, NWH, false, false);
       const uint32_t idW0 = umma::idesc_tf32(128, tp.N0w, false, false);
-      // one GEMM of `nch` chunks with `ks` (last chunk: ks_last) k steps into accumulator region `acc` (0: F / B, 1: W);
-      // split: the lo*hi and hi*lo products go to their own accumulator (forward GEMMs)
-      auto gemm = [&](int nch, int ks_last, uint32_t idesc, int cgsB, int acc, bool split) {
-        mbar_wait_parked(&bars->accfree[acc], (accuse[acc] & 1u) ^ 1u);
-        accuse[acc]++;
+      // one GEMM of `nch` chunks (last chunk: ks_last k steps) of tile slot ti into accumulator region `acc` (0: F / B,
+      // 1: W); split: the lo*hi and hi*lo products go to their own accumulator (forward GEMMs)
+      int prof_k = 0;
+      auto gemm = [&](int ti, int nch, int ks_last, uint32_t idesc, int cgsB, int acc, bool split) {
+        const int bi = 2 * ti + acc;
+        TU_MARK(1, prof_k, ti, 0 + 8 * acc);
+        mbar_wait(&bars->accfree[bi], (accuse[bi] & 1u) ^ 1u);
+        accuse[bi]++;
         umma::fence_after_sync();
-        const uint32_t dbig = umma::tmem_addr(tbase, 0, acc == 0 ? COL_BIG : COL_W);
-        const uint32_t dsml = split ? umma::tmem_addr(tbase, 0, COL_SMALL) : dbig;
+        const uint32_t dbig = umma::tmem_addr(tbase, 0, acc == 0 ? col_big(ti) : col_w(ti));
+        const uint32_t dsml = split ? umma::tmem_addr(tbase, 0, col_small(ti)) : dbig;
         const uint32_t halfB = 8u * cgsB;
         for (int ch = 0; ch < nch; ++ch, ++cc) {
           const uint32_t st = cc % TU_NS, use = cc / TU_NS;
-          mbar_wait_parked(&bars->fullA[st], use & 1u);
-          mbar_wait_parked(&bars->fullB[st], use & 1u);
+          mbar_wait(&bars->fullA[st], use & 1u);         // one thread: spinning is cheap and wakes up at once
+          mbar_wait(&bars->fullB[st], use & 1u);
           umma::fence_after_sync();
+          if (ch == 0) TU_MARK(1, prof_k, ti, 1 + 8 * acc);
           const uint32_t a0 = ringA + st * TU_ASTAGE, b0 = ringB + st * tp.b_stage;
           const int ks = ch == nch - 1 ? ks_last : 4;
           for (int k = 0; k < ks; ++k) {
@@ -289,20 +332,27 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           umma::commit(&bars->emptyA[st]);
           umma::commit(&bars->emptyB[st]);
         }
-        umma::commit(&bars->accfull[acc]);
+        umma::commit(&bars->accfull[bi]);
+        TU_MARK(1, prof_k, ti, 2 + 8 * acc);
       };
+      const int ks0 = (tp.K0p - 32 * (tp.nK0 - 1)) / 8;
       for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
         const int s = item % S;
         const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
-        for (long long t = t0; t < t1; ++t) {
-          const int ks0 = (tp.K0p - 32 * (tp.nK0 - 1)) / 8;
-          gemm(tp.nK0, ks0, idF, tu_cgs(HW), 0, true);
-          for (int l = 1; l < G; ++l) gemm(nH, 4, idF, tu_cgs(HW), 0, true);
-          for (int l = G - 1; l >= 1; --l) {
-            gemm(nH, 4, idF, tu_cgs(HW), 0, false);         // B_l: dA_{l-1}
-            gemm(4, 4, idWh, tu_cgs(NWH), 1, false);        // W_l
+        for (long long tb = t0; tb < t1; tb += NT) {
+          const int ntl = NT == 1 ? 1 : (int)((t1 - tb) < NT ? (t1 - tb) : NT);
+          for (int k = 0; k < 2 * G; ++k) {
+            for (int ti = 0; ti < ntl; ++ti) {
+              prof_k = k;
+              if (k == 0) gemm(ti, tp.nK0, ks0, idF, tu_cgs(HW), 0, true);
+              else if (k < G) gemm(ti, nH, 4, idF, tu_cgs(HW), 0, true);
+              else {
+                const int l = 2 * G - 1 - k;
+                if (l >= 1) gemm(ti, nH, 4, idF, tu_cgs(HW), 0, false);                                  // B_l: dA_{l-1}
+                gemm(ti, 4, 4, l >= 1 ? idWh : idW0, l >= 1 ? tu_cgs(NWH) : tu_cgs(tp.N0w), 1, false);    // W_l
+              }
+            }
           }
-          gemm(4, 4, idW0, tu_cgs(tp.N0w), 1, false);       // W_0
         }
       }
     }
@@ -313,26 +363,27 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
     const int r = 32 * wq + lane;                        // row of the tile = TMEM lane
     const int cb = grp * HH;                             // first column of this thread
     const uint32_t lane_t = (uint32_t)(32 * wq) << 16;
-    uint32_t cc = 0, accuse[2] = {0u, 0u};
+    uint32_t cc = 0, accuse[4] = {0u, 0u, 0u, 0u};
     float* bias_s = par + tp.par_bias;                   // [G][HW]
     float* slope_s = par + tp.par_slope;                 // [G][HW] effective negative-side slope
     float* sfac_s = par + tp.par_sraw;                   // [G][HW] d(effective slope)/d(parameter): 2 s or 1
     float* wl_s = par + tp.par_wl;                       // [OUT][HW], then bias [4]
     float* accl_s = par + tp.par_accl + wq * (OUT * HW + 4);   // per warp quarter [OUT][HW] + [4]: gradient of the last
                                                          // block (summed in fixed order at the end: reruns are bit-identical)
-    float* fx_s = par + tp.par_fx;                       // [2][128][4]: partial outputs of the two column groups
     const BlockPlan& bL = mp.b[G];
-    float* scr = scratch + (size_t)blockIdx.x * tp.scratch_cta;
+    double stat = 0.0;
+    float* gout = nullptr;
 
-    auto wait_acc = [&](int a) {
-      mbar_wait_parked(&bars->accfull[a], accuse[a] & 1u);
-      accuse[a]++;
+    auto wait_acc = [&](int ti, int a) {
+      const int bi = 2 * ti + a;
+      mbar_wait_parked(&bars->accfull[bi], accuse[bi] & 1u);
+      accuse[bi]++;
       umma::fence_after_sync();
     };
-    auto free_acc = [&](int a) {                          // this warp has read its share of accumulator region a
+    auto free_acc = [&](int ti, int a) {                  // this warp has read its share of that accumulator region
       umma::fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->accfree[a]);
+      if (lane == 0) mbar_arrive(&bars->accfree[2 * ti + a]);
     };
     // Ring A protocol: EVERY row-worker warp takes part in EVERY chunk, in order -- slot() waits for the slot's release,
     // the owner(s) write, done() arrives (8 arrivals complete a chunk).  A warp that skipped the chunks it does not
@@ -343,17 +394,98 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       mbar_wait_parked(&bars->emptyA[st], (use & 1u) ^ 1u);
       return st;
     };
-    auto done = [&](uint32_t st) {
-      fence_proxy_async();
+    auto done = [&](uint32_t st, bool wrote) {
+      if (wrote) fence_proxy_async();                    // only the warps that wrote operand bytes need the proxy fence
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->fullA[st]);
+    };
+    // K-major chunks of this thread's columns (values v[0..HH)) as the A operand of a hidden-width GEMM
+    auto put_chunks = [&](const float* v) {
+#pragma unroll
+      for (int jj = 0; jj < nH; ++jj) {
+        const uint32_t st = slot(cc + jj);
+        if (jj / nHH == grp) put_row_chunk(ringA + st * TU_ASTAGE, r, v + 32 * (jj % nHH));
+        done(st, jj / nHH == grp);
+      }
+      cc += nH;
+    };
+    // drain a weight-gradient GEMM of block `lb` (>= 1): operand row m = TMEM lane = output feature; the two column
+    // groups split the input features, group 1 also takes the constant-one column (bias, slopes)
+    auto drain_hidden = [&](int ti, int lb) {
+      const BlockPlan& bp = mp.b[lb];
+      wait_acc(ti, 1);
+      if (r < HW) {
+        float* gw = gout + bp.pw + r * bp.ld_in + cb;
+#pragma unroll 1
+        for (int n0 = 0; n0 < HH; n0 += 16) {
+          float v[16];
+          umma::tmem_ld16(tbase + lane_t + col_w(ti) + cb + n0, v);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) red_add4(gw + n0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+      if (grp == 1) {
+        float v[8];
+        umma::tmem_ld8(tbase + lane_t + col_w(ti) + HW, v);
+        umma::tmem_ld_wait();
+        if (r < HW) red_add1(gout + bp.pb + r, v[0]);
+        else if (STACKQ && act_has_slopes(bp.act)) red_add1(gout + bp.ps + (r - HW), v[0] * sfac_s[lb * HW + (r - HW)]);
+      }
+      free_acc(ti, 1);
+    };
+    // operands produced once dZ_l of a tile is known: B_l (l >= 1) and W_l
+    auto bwd_produce = [&](int l, int ti, bool valid, const float* xrow, const float* dz, const float* qv) {
+      float* scr = scratch + ((size_t)blockIdx.x * NT + ti) * tp.scratch_cta;
+      if (l >= 1) put_chunks(dz);                          // dA_{l-1} = dZ_l W_l: critical path first
+      if (tid == 0) TU_MARK(0, 60 + l, ti, 4);
+      if (l < G - 1) drain_hidden(ti, l + 1);              // W_{l+1} of this tile, before its accumulator is reused
+      if (tid == 0) TU_MARK(0, 60 + l, ti, 5);
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {                        // W_l: chunk q = the 32 rows of lane quarter q
+        const uint32_t st = slot(cc + q);
+        if (q == wq) {
+          const uint32_t sa = ringA + st * TU_ASTAGE, sb = ringB + st * tp.b_stage;
+#pragma unroll
+          for (int j = 0; j < HH; ++j) put_t(sa, TU_HALFA, TU_CGA, cb + j, lane, dz[j]);
+          if (HW == 64) {
+#pragma unroll
+            for (int j = 0; j < HH; ++j) put_t(sa, TU_HALFA, TU_CGA, 64 + cb + j, lane, STACKQ ? qv[STACKQ ? j : 0] : 0.f);
+          }
+          if (l >= 1) {
+            const int cgs = tu_cgs(NWH), half = tu_half(NWH);
+            const float* sc = scr + (size_t)(l - 1) * HW * 128;
+            const float* sl = slope_s + (l - 1) * HW + cb;
+            float4 kv[HH / 4];
+#pragma unroll
+            for (int g4 = 0; g4 < HH / 4; ++g4) kv[g4] = *reinterpret_cast<const float4*>(sc + ((size_t)(cb / 4 + g4) * 128 + r) * 4);
+#pragma unroll
+            for (int g4 = 0; g4 < HH / 4; ++g4) {
+              const float k4[4] = {kv[g4].x, kv[g4].y, kv[g4].z, kv[g4].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                put_t(sb, half, cgs, cb + 4 * g4 + i, lane, tu_from_keep<ACTK>(hact, k4[i], SLOPES ? sl[4 * g4 + i] : 0.f));
+            }
+            if (grp == 1) put_t(sb, half, cgs, HW, lane, 1.f);
+          } else if (grp == 0) {
+            const int cgs = tu_cgs(tp.N0w), half = tu_half(tp.N0w);
+            for (int k = 0; k < D; ++k) put_t(sb, half, cgs, k, lane, valid ? xrow[k] : 0.f);
+            put_t(sb, half, cgs, D, lane, 1.f);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->fullB[st]);
+        }
+        done(st, false);                                   // the owner fenced above
+      }
+      cc += 4;
     };
 
     for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
       const int c = item / S, s = item - c * S;
       const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
       const float* th = theta_pad + (size_t)c * mp.Ppad;
-      float* gout = partial + ((size_t)c * S + s) * mp.Ppad;
+      gout = partial + ((size_t)c * S + s) * mp.Ppad;
       ew_barrier();                                      // previous item's parameters are dead
       for (int e = tid; e < G * HW; e += 256) {
         const int l = e / HW, j = e - l * HW;
@@ -377,288 +509,229 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       for (int i = 4 * tid; i < mp.Ppad; i += 4 * 256) *reinterpret_cast<float4*>(gout + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       __threadfence();
       ew_barrier();
-      double stat = 0.0;
+      stat = 0.0;
 
-      for (long long t = t0; t < t1; ++t) {
-        const long long row = t * 128 + r;
-        const bool valid = row < N;
-        const float* xrow = X + (valid ? row : 0) * (long long)D;
-        // ------------------------------------------------ F_0 operand: this row of X (column group 0)
-        for (int ch = 0; ch < tp.nK0; ++ch) {
-          const uint32_t st = slot(cc + ch);
-          if (grp == 0) {
-            const uint32_t stage = ringA + st * TU_ASTAGE;
-            const int ngr = min(8, (tp.K0p - 32 * ch) >> 2);
-            for (int kq = 0; kq < ngr; ++kq) {
-              float h[4], l4[4];
+      for (long long tb = t0; tb < t1; tb += NT) {
+        const int ntl = NT == 1 ? 1 : (int)((t1 - tb) < NT ? (t1 - tb) : NT);
+        for (int k = 0; k <= 2 * G; ++k) {
+#pragma unroll 1
+          for (int ti_ = 0; ti_ < ntl; ++ti_) {
+            const int ti = NT == 1 ? 0 : ti_;              // a compile-time constant when one tile is in flight
+            const long long row = (tb + ti) * 128 + r;
+            const bool valid = row < N;
+            const float* xrow = X + (valid ? row : 0) * (long long)D;
+            float* scr = scratch + ((size_t)blockIdx.x * NT + ti) * tp.scratch_cta;
+            if (tid == 0) TU_MARK(0, k, ti, 0);
+            float dz[HH];                                     // values of this thread's columns (z / kept value / dZ)
+            float qv[STACKQ ? HH : 1];
+            int bl = -1;                                      // block whose dZ this segment produced (-1: none)
+            if (k == 0) {
+              // ------------------------------------------------ F_0 operand: this row of X (column group 0)
+              for (int ch = 0; ch < tp.nK0; ++ch) {
+                const uint32_t st = slot(cc + ch);
+                if (grp == 0) {
+                  const uint32_t stage = ringA + st * TU_ASTAGE;
+                  const int ngr = min(8, (tp.K0p - 32 * ch) >> 2);
+                  for (int kq = 0; kq < ngr; ++kq) {
+                    float h[4], l4[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int k = 32 * ch + 4 * kq + i;
-                const float x = (valid && k < D) ? xrow[k] : 0.f;
-                umma::split_tf32_fast(x, h[i], l4[i]);
-              }
-              const uint32_t a = stage + kq * TU_CGA + r * 16;
-              sts128(a, h[0], h[1], h[2], h[3]);
-              sts128(a + TU_HALFA, l4[0], l4[1], l4[2], l4[3]);
-            }
-          }
-          done(st);
-        }
-        cc += tp.nK0;
-        // ------------------------------------------------ forward through the hidden blocks
-        float dz[HH];                                   // values of this thread's columns (z / kept value / dZ)
-        float qv[STACKQ ? HH : 1];
-        for (int l = 0; l < G; ++l) {
-          wait_acc(0);
-#pragma unroll
-          for (int j = 0; j < nHH; ++j) {
-            float vb[32], vs[32];
-            tmem_ld32(tbase + lane_t + COL_BIG + cb + 32 * j, vb);
-            tmem_ld32(tbase + lane_t + COL_SMALL + cb + 32 * j, vs);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dz[32 * j + i] = vb[i] + vs[i];
-          }
-          free_acc(0);
-          const float* bz = bias_s + l * HW + cb;
-          const float* sl = slope_s + l * HW + cb;
-          if (l < G - 1) {
-            float* sc = scr + (size_t)l * HW * 128;
-#pragma unroll
-            for (int q4 = 0; q4 < HH / 4; ++q4) {
-              float keep[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int col = 4 * q4 + i;
-                const float z = dz[col] + bz[col];
-                const float a = tu_act<ACTK>(hact, z, SLOPES ? sl[col] : 0.f);
-                keep[i] = tu_keep<ACTK>(hact, z, a);
-                dz[col] = a;
-              }
-              *reinterpret_cast<float4*>(sc + ((size_t)(cb / 4 + q4) * 128 + r) * 4) = make_float4(keep[0], keep[1], keep[2], keep[3]);
-            }
-#pragma unroll
-            for (int jj = 0; jj < nH; ++jj) {
-              const uint32_t st = slot(cc + jj);
-              if (jj / nHH == grp) put_row_chunk(ringA + st * TU_ASTAGE, r, &dz[32 * (jj % nHH)]);
-              done(st);
-            }
-            cc += nH;
-          } else {
-            // ---------------------------------------------- last hidden block, last block, likelihood
-            float f[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int col = 0; col < HH; ++col) {
-              const float z = dz[col] + bz[col];
-              const float a = tu_act<ACTK>(hact, z, SLOPES ? sl[col] : 0.f);
-              dz[col] = tu_keep<ACTK>(hact, z, a);
-#pragma unroll
-              for (int o = 0; o < 4; ++o)
-                if (o < OUT) f[o] = fmaf(wl_s[o * HW + cb + col], a, f[o]);
-            }
-            *reinterpret_cast<float4*>(fx_s + (grp * 128 + r) * 4) = make_float4(f[0], f[1], f[2], f[3]);
-            ew_barrier();
-            {
-              const float4 o4 = *reinterpret_cast<const float4*>(fx_s + ((grp ^ 1) * 128 + r) * 4);
-              // fixed order (group 0 + group 1) so both threads of a row get identical bits
-              const float4 m4 = make_float4(f[0], f[1], f[2], f[3]);
-              const float4 a4 = grp == 0 ? m4 : o4, b4 = grp == 0 ? o4 : m4;
-              f[0] = a4.x + b4.x; f[1] = a4.y + b4.y; f[2] = a4.z + b4.z; f[3] = a4.w + b4.w;
-            }
-            float dfl[4] = {0.f, 0.f, 0.f, 0.f};
-            const float lo = 1e-8f, hi = (float)(1 - 1e-7);          // likelihood.py:229-230
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              if (o < OUT) {
-                const float fo = act_fwd<float>(bL.act, f[o] + wl_s[OUT * HW + o], 0.f);
-                if (valid) {
-                  const float y = Y[row * (long long)OUT + o];
-                  float df;
-                  if (mp.lik == LIK_BERN) {
-                    const float p = fo < lo ? lo : (fo > hi ? hi : fo);
-                    if (grp == 0) stat += (double)((1.f - y) * log1pf(-p) + y * logf(p));
-                    df = (fo < lo || fo > hi) ? 0.f : (y / p - (1.f - y) / (1.f - p));
-                  } else {
-                    const float res = y - fo;
-                    if (grp == 0) stat += (double)res * (double)res;
-                    df = res;
+                    for (int i = 0; i < 4; ++i) {
+                      const int kk = 32 * ch + 4 * kq + i;
+                      const float x = (valid && kk < D) ? xrow[kk] : 0.f;
+                      umma::split_tf32_fast(x, h[i], l4[i]);
+                    }
+                    const uint32_t a = stage + kq * TU_CGA + r * 16;
+                    sts128(a, h[0], h[1], h[2], h[3]);
+                    sts128(a + TU_HALFA, l4[0], l4[1], l4[2], l4[3]);
                   }
-                  dfl[o] = df * act_deriv_from_out<float>(bL.act, fo);
                 }
+                done(st, grp == 0);
               }
-            }
-            // gradient of the last block (column sums over the tile's rows), dA_{G-1}, dZ_{G-1}
+              cc += tp.nK0;
+            } else if (k <= G) {
+              // ------------------------------------------------ epilogue of F_l
+              const int l = k - 1;
+              float yv[4] = {0.f, 0.f, 0.f, 0.f};
+              if (l == G - 1 && valid) {                       // targets requested before the accumulator wait
 #pragma unroll
-            for (int g = 0; g < nHH; ++g) {
+                for (int o = 0; o < 4; ++o)
+                  if (o < OUT) yv[o] = Y[row * (long long)OUT + o];
+              }
+              wait_acc(ti, 0);
+              if (tid == 0) TU_MARK(0, k, ti, 1);
 #pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                if (o < OUT) {
-                  float pr[32];
+              for (int j = 0; j < nHH; ++j) {
+                float vb[32], vs[32];
+                tmem_ld32(tbase + lane_t + col_big(ti) + cb + 32 * j, vb);
+                tmem_ld32(tbase + lane_t + col_small(ti) + cb + 32 * j, vs);
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) pr[i] = dfl[o] * tu_from_keep<ACTK>(hact, dz[32 * g + i], SLOPES ? sl[32 * g + i] : 0.f);
-                  const float cs = colsum32(pr, lane);
-                  accl_s[o * HW + cb + 32 * g + lane] += cs;
+                for (int i = 0; i < 32; ++i) dz[32 * j + i] = vb[i] + vs[i];
+              }
+              free_acc(ti, 0);
+              const float* bz = bias_s + l * HW + cb;
+              const float* sl = slope_s + l * HW + cb;
+              if (l < G - 1) {
+                float* sc = scr + (size_t)l * HW * 128;
+#pragma unroll
+                for (int q4 = 0; q4 < HH / 4; ++q4) {
+                  float keep[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const int col = 4 * q4 + i;
+                    const float z = dz[col] + bz[col];
+                    const float a = tu_act<ACTK>(hact, z, SLOPES ? sl[col] : 0.f);
+                    keep[i] = tu_keep<ACTK>(hact, z, a);
+                    dz[col] = a;
+                  }
+                  *reinterpret_cast<float4*>(sc + ((size_t)(cb / 4 + q4) * 128 + r) * 4) = make_float4(keep[0], keep[1], keep[2], keep[3]);
                 }
+                put_chunks(dz);
+              } else {
+                // ---------------------------------------------- last hidden block, last block, likelihood
+                float* fx_s = par + tp.par_fx + ti * (2 * 128 * 4);
+                float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int col = 0; col < HH; ++col) {
+                  const float z = dz[col] + bz[col];
+                  const float a = tu_act<ACTK>(hact, z, SLOPES ? sl[col] : 0.f);
+                  dz[col] = tu_keep<ACTK>(hact, z, a);
+#pragma unroll
+                  for (int o = 0; o < 4; ++o)
+                    if (o < OUT) f[o] = fmaf(wl_s[o * HW + cb + col], a, f[o]);
+                }
+                *reinterpret_cast<float4*>(fx_s + (grp * 128 + r) * 4) = make_float4(f[0], f[1], f[2], f[3]);
+                ew_barrier();
+                {
+                  const float4 o4 = *reinterpret_cast<const float4*>(fx_s + ((grp ^ 1) * 128 + r) * 4);
+                  // fixed order (group 0 + group 1) so both threads of a row get identical bits
+                  const float4 m4 = make_float4(f[0], f[1], f[2], f[3]);
+                  const float4 a4 = grp == 0 ? m4 : o4, b4 = grp == 0 ? o4 : m4;
+                  f[0] = a4.x + b4.x; f[1] = a4.y + b4.y; f[2] = a4.z + b4.z; f[3] = a4.w + b4.w;
+                }
+                float dfl[4] = {0.f, 0.f, 0.f, 0.f};
+                const float lo = 1e-8f, hi = (float)(1 - 1e-7);          // likelihood.py:229-230
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                  if (o < OUT) {
+                    const float fo = act_fwd<float>(bL.act, f[o] + wl_s[OUT * HW + o], 0.f);
+                    if (valid) {
+                      const float y = yv[o];
+                      float df;
+                      if (mp.lik == LIK_BERN) {
+                        const float p = fo < lo ? lo : (fo > hi ? hi : fo);
+                        if (grp == 0) stat += (double)((1.f - y) * log1pf(-p) + y * logf(p));
+                        df = (fo < lo || fo > hi) ? 0.f : (y / p - (1.f - y) / (1.f - p));
+                      } else {
+                        const float res = y - fo;
+                        if (grp == 0) stat += (double)res * (double)res;
+                        df = res;
+                      }
+                      dfl[o] = df * act_deriv_from_out<float>(bL.act, fo);
+                    }
+                  }
+                }
+                // gradient of the last block (column sums over the tile's rows), dA_{G-1}, dZ_{G-1}
+#pragma unroll
+                for (int g = 0; g < nHH; ++g) {
+#pragma unroll
+                  for (int o = 0; o < 4; ++o) {
+                    if (o < OUT) {
+                      float pr[32];
+#pragma unroll
+                      for (int i = 0; i < 32; ++i) pr[i] = dfl[o] * tu_from_keep<ACTK>(hact, dz[32 * g + i], SLOPES ? sl[32 * g + i] : 0.f);
+                      const float cs = colsum32(pr, lane);
+                      accl_s[o * HW + cb + 32 * g + lane] += cs;
+                    }
+                  }
+                }
+                if (grp == 0) {
+                  float bsum[4];
+#pragma unroll
+                  for (int o = 0; o < 4; ++o) {
+                    float v = dfl[o];
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+                    bsum[o] = v;
+                  }
+                  if (lane == 0)
+                    for (int o = 0; o < OUT; ++o) accl_s[OUT * HW + o] += bsum[o];
+                }
+#pragma unroll
+                for (int kk = 0; kk < HH; ++kk) {
+                  float dA = 0.f;
+#pragma unroll
+                  for (int o = 0; o < 4; ++o)
+                    if (o < OUT) dA = fmaf(dfl[o], wl_s[o * HW + cb + kk], dA);
+                  const float sk = dz[kk];
+                  if (STACKQ) qv[STACKQ ? kk : 0] = sk < 0.f ? sk * dA : 0.f;
+                  dz[kk] = dA * tu_deriv<ACTK>(hact, sk, SLOPES ? sl[kk] : 0.f);
+                }
+                bl = G - 1;
               }
-            }
-            if (grp == 0) {
-              float bsum[4];
-#pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                float v = dfl[o];
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
-                bsum[o] = v;
-              }
-              if (lane == 0)
-                for (int o = 0; o < OUT; ++o) accl_s[OUT * HW + o] += bsum[o];
-            }
-#pragma unroll
-            for (int k = 0; k < HH; ++k) {
-              float dA = 0.f;
-#pragma unroll
-              for (int o = 0; o < 4; ++o)
-                if (o < OUT) dA = fmaf(dfl[o], wl_s[o * HW + cb + k], dA);
-              const float sk = dz[k];
-              if (STACKQ) qv[STACKQ ? k : 0] = sk < 0.f ? sk * dA : 0.f;
-              dz[k] = dA * tu_deriv<ACTK>(hact, sk, SLOPES ? sl[k] : 0.f);
-            }
-          }
-        }
-        // ------------------------------------------------ backward
-        for (int l = G - 1; l >= 0; --l) {
-          // (1) dZ_l as the A operand of B_l (dA_{l-1} = dZ_l W_l): critical path first
-          if (l >= 1) {
-#pragma unroll
-            for (int jj = 0; jj < nH; ++jj) {
-              const uint32_t st = slot(cc + jj);
-              if (jj / nHH == grp) put_row_chunk(ringA + st * TU_ASTAGE, r, &dz[32 * (jj % nHH)]);
-              done(st);
-            }
-            cc += nH;
-          }
-          // (2) drain the previous weight-gradient GEMM (W_{l+1}): operand row m = TMEM lane = output feature; the two
-          //     column groups split the input features, group 1 also takes the constant-one column (bias, slopes)
-          if (l < G - 1) {
-            const BlockPlan& bp = mp.b[l + 1];
-            wait_acc(1);
-            if (r < HW) {
-              float* gw = gout + bp.pw + r * bp.ld_in + cb;
-#pragma unroll 1
-              for (int n0 = 0; n0 < HH; n0 += 16) {
-                float v[16];
-                umma::tmem_ld16(tbase + lane_t + COL_W + cb + n0, v);
-                umma::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) red_add4(gw + n0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-              }
-            }
-            if (grp == 1) {
-              float v[8];
-              umma::tmem_ld8(tbase + lane_t + COL_W + HW, v);
-              umma::tmem_ld_wait();
-              if (r < HW) red_add1(gout + bp.pb + r, v[0]);
-              else if (STACKQ && act_has_slopes(bp.act)) red_add1(gout + bp.ps + (r - HW), v[0] * sfac_s[(l + 1) * HW + (r - HW)]);
-            }
-            free_acc(1);
-          }
-          // (3) operands of W_l, chunk wq = the 32 rows of this lane quarter; the two column groups split the operand rows
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t st = slot(cc + q);
-            if (q == wq) {
-            const uint32_t sa = ringA + st * TU_ASTAGE, sb = ringB + st * tp.b_stage;
-#pragma unroll
-            for (int j = 0; j < HH; ++j) put_t(sa, TU_HALFA, TU_CGA, cb + j, lane, dz[j]);
-            if (HW == 64) {
-#pragma unroll
-              for (int j = 0; j < HH; ++j) put_t(sa, TU_HALFA, TU_CGA, 64 + cb + j, lane, STACKQ ? qv[STACKQ ? j : 0] : 0.f);
-            }
-            if (l >= 1) {
-              const int cgs = tu_cgs(NWH), half = tu_half(NWH);
-              const float* sc = scr + (size_t)(l - 1) * HW * 128;
-              const float* sl = slope_s + (l - 1) * HW + cb;
+            } else if (k < 2 * G) {
+              // ------------------------------------------------ epilogue of B_lp: dA_{lp-1} -> dZ_{lp-1}
+              const int lp = 2 * G - k;
+              const float* sc = scr + (size_t)(lp - 1) * HW * 128;
+              const float* sl = slope_s + (lp - 1) * HW + cb;
               float4 kv[HH / 4];
 #pragma unroll
               for (int g4 = 0; g4 < HH / 4; ++g4) kv[g4] = *reinterpret_cast<const float4*>(sc + ((size_t)(cb / 4 + g4) * 128 + r) * 4);
+              wait_acc(ti, 0);
+              if (tid == 0) TU_MARK(0, k, ti, 1);
+#pragma unroll
+              for (int j = 0; j < nHH; ++j) {
+                float v[32];
+                tmem_ld32(tbase + lane_t + col_big(ti) + cb + 32 * j, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dz[32 * j + i] = v[i];
+              }
+              free_acc(ti, 0);
 #pragma unroll
               for (int g4 = 0; g4 < HH / 4; ++g4) {
                 const float k4[4] = {kv[g4].x, kv[g4].y, kv[g4].z, kv[g4].w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  put_t(sb, half, cgs, cb + 4 * g4 + i, lane, tu_from_keep<ACTK>(hact, k4[i], SLOPES ? sl[4 * g4 + i] : 0.f));
-              }
-              if (grp == 1) put_t(sb, half, cgs, HW, lane, 1.f);
-            } else if (grp == 0) {
-              const int cgs = tu_cgs(tp.N0w), half = tu_half(tp.N0w);
-              for (int k = 0; k < D; ++k) put_t(sb, half, cgs, k, lane, valid ? xrow[k] : 0.f);
-              put_t(sb, half, cgs, D, lane, 1.f);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->fullB[st]);
-            }
-            done(st);
-          }
-          cc += 4;
-          // (4) dA_{l-1} from tensor memory -> dZ_{l-1}
-          if (l >= 1) {
-            const float* sc = scr + (size_t)(l - 1) * HW * 128;
-            const float* sl = slope_s + (l - 1) * HW + cb;
-            float4 kv[HH / 4];
-#pragma unroll
-            for (int g4 = 0; g4 < HH / 4; ++g4) kv[g4] = *reinterpret_cast<const float4*>(sc + ((size_t)(cb / 4 + g4) * 128 + r) * 4);
-            wait_acc(0);
-#pragma unroll
-            for (int j = 0; j < nHH; ++j) {
-              float v[32];
-              tmem_ld32(tbase + lane_t + COL_BIG + cb + 32 * j, v);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) dz[32 * j + i] = v[i];
-            }
-            free_acc(0);
-#pragma unroll
-            for (int g4 = 0; g4 < HH / 4; ++g4) {
-              const float k4[4] = {kv[g4].x, kv[g4].y, kv[g4].z, kv[g4].w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int col = 4 * g4 + i;
-                const float dA = dz[col];
-                if (STACKQ) qv[STACKQ ? col : 0] = k4[i] < 0.f ? k4[i] * dA : 0.f;
-                dz[col] = dA * tu_deriv<ACTK>(hact, k4[i], SLOPES ? sl[col] : 0.f);
-              }
-            }
-          }
-        }
-        // ------------------------------------------------ drain W_0
-        {
-          const BlockPlan& b0 = mp.b[0];
-          wait_acc(1);
-          if (grp == 0) {
-            if (r < HW) {
-              float* gw = gout + b0.pw + r * b0.ld_in;
-              for (int n0 = 0; n0 < tp.N0w; n0 += 8) {
-                float v[8];
-                umma::tmem_ld8(tbase + lane_t + COL_W + n0, v);
-                umma::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int n = n0 + i;
-                  if (n < D) red_add1(gw + n, v[i]);
-                  else if (n == D) red_add1(gout + b0.pb + r, v[i]);
+                for (int i = 0; i < 4; ++i) {
+                  const int col = 4 * g4 + i;
+                  const float dA = dz[col];
+                  if (STACKQ) qv[STACKQ ? col : 0] = k4[i] < 0.f ? k4[i] * dA : 0.f;
+                  dz[col] = dA * tu_deriv<ACTK>(hact, k4[i], SLOPES ? sl[col] : 0.f);
                 }
               }
-            } else if (STACKQ && act_has_slopes(b0.act)) {
-              float v[8];
-              umma::tmem_ld8(tbase + lane_t + COL_W + (D & ~7), v);
-              umma::tmem_ld_wait();
-              float pick = 0.f;
+              bl = lp - 1;
+            } else {
+              // ------------------------------------------------ drain W_0
+              const BlockPlan& b0 = mp.b[0];
+              wait_acc(ti, 1);
+              if (grp == 0) {
+                if (r < HW) {
+                  float* gw = gout + b0.pw + r * b0.ld_in;
+                  for (int n0 = 0; n0 < tp.N0w; n0 += 8) {
+                    float v[8];
+                    umma::tmem_ld8(tbase + lane_t + col_w(ti) + n0, v);
+                    umma::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (i == (D & 7)) pick = v[i];
-              red_add1(gout + b0.ps + (r - HW), pick * sfac_s[r - HW]);
+                    for (int i = 0; i < 8; ++i) {
+                      const int n = n0 + i;
+                      if (n < D) red_add1(gw + n, v[i]);
+                      else if (n == D) red_add1(gout + b0.pb + r, v[i]);
+                    }
+                  }
+                } else if (STACKQ && act_has_slopes(b0.act)) {
+                  float v[8];
+                  umma::tmem_ld8(tbase + lane_t + col_w(ti) + (D & ~7), v);
+                  umma::tmem_ld_wait();
+                  float pick = 0.f;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (i == (D & 7)) pick = v[i];
+                  red_add1(gout + b0.ps + (r - HW), pick * sfac_s[r - HW]);
+                }
+              }
+              free_acc(ti, 1);
             }
+            if (bl >= 0) bwd_produce(bl, ti, valid, xrow, dz, qv);   // one inlined copy for both kinds of segment
+            if (tid == 0) TU_MARK(0, k, ti, 3);
           }
-          free_acc(1);
         }
       }
       // ---------------------------------------------------- item epilogue: last block gradient, statistic
@@ -721,9 +794,9 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   tp.b_stage = std::max(chunk, std::max(2 * tu_half(HW + 16), 2 * tu_half(tp.N0w)));
   tp.b_stage = tu_pad(tp.b_stage, 128);
   int off = 0;
-  tp.off_a = off; off += TU_NS * tp.a_stage;
+  tp.off_a = off; off += tu_ns(HW) * tp.a_stage;
   off = tu_pad(off, 128);
-  tp.off_b = off; off += TU_NS * tp.b_stage;
+  tp.off_b = off; off += tu_ns(HW) * tp.b_stage;
   tp.off_par = off;
   int pf = 0;
   tp.par_bias = pf; pf += G * HW;
@@ -731,17 +804,34 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   tp.par_sraw = pf; pf += G * HW;
   tp.par_wl = pf; pf += mp.OUT * HW + 4;
   tp.par_accl = pf; pf += 4 * (mp.OUT * HW + 4) + 16;    // one per lane quarter, + 8 doubles of reduction scratch
-  tp.par_fx = pf; pf += 2 * 128 * 4;
+  tp.par_fx = pf; pf += 2 * 2 * 128 * 4;                 // [tile slot][column group][row][4]
   off += pf * 4;
   off = tu_pad(off, 16);
   tp.off_bar = off; off += (int)sizeof(TuBars);
   tp.smem_bytes = off;
-  tp.scratch_cta = (G - 1) * HW * 128;
+  tp.scratch_cta = (G - 1) * HW * 128;                   // per tile slot
   return (size_t)off <= smem_limit;
 }
 
+#ifdef TBNN_TU_PROFILE
+extern "C" int tbnn_tu_profile(long long* out, int cap) {
+  // out: [role][tag | clock][cap]; returns entries of role 0 in the low 16 bits, role 1 in the high 16 bits
+  static long long buf[2][2][4096];
+  int n[2];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(buf, g_tu_prof, sizeof(buf));
+  cudaMemcpyFromSymbol(n, g_tu_prof_n, sizeof(n));
+  for (int r = 0; r < 2; ++r)
+    for (int q = 0; q < 2; ++q)
+      for (int i = 0; i < cap && i < 4096; ++i) out[(r * 2 + q) * cap + i] = buf[r][q][i];
+  int zero[2] = {0, 0};
+  cudaMemcpyToSymbol(g_tu_prof_n, zero, sizeof(zero));
+  return n[0] | (n[1] << 16);
+}
+#endif
+
 size_t train_umma_wimg_bytes(const TrainUmmaPlan& tp, int C) { return (size_t)C * tp.wimg_chain; }
-size_t train_umma_scratch_bytes(const TrainUmmaPlan& tp, int num_sms) { return (size_t)num_sms * tp.scratch_cta * 4; }
+size_t train_umma_scratch_bytes(const TrainUmmaPlan& tp, int num_sms) { return (size_t)num_sms * 2 * tp.scratch_cta * 4; }   // two tile slots
 
 void launch_train_umma(const ModelPlan& mp, const TrainUmmaPlan& tp, int num_sms, int C, int S, const float* theta_pad,
                        unsigned char* wimg, float* scratch, const float* X, const float* Y, long long N,
