@@ -346,12 +346,12 @@ def _stdout_to_stderr():
 
 
 def tune_step_size(eng, th, hy, eps0, L, rank):
-    """Per-chain step sizes at which the chains move: halve a chain's step size until a short trajectory is accepted
-    with probability >= 0.5 (the reference tunes the step size as well, with its paramAdapter)."""
+    """Per-chain step sizes at which the chains move: halve a chain's step size until a full L-step trajectory from the
+    start state is accepted with probability >= 0.5 (the reference tunes the step size as well, with its paramAdapter)."""
     C = th.shape[0]
     eps = np.full(C, float(eps0))
     stats = torch.zeros(C, 4, dtype=th.dtype, device=th.device)
-    Lt = max(2, min(L, 10))
+    Lt = L
     for it in range(24):
         trial = th.clone()
         eng.hmc_step(trial, hy, 77 + rank, 1000 + it, eps, Lt, stats=stats)
@@ -426,8 +426,15 @@ def main():
 
     # ---------------- step sizes at which the chains move (untimed), then warm-up
     eps = np.full(C, float(cfg["eps"])) if args.no_tune else tune_step_size(eng, th, hy, cfg["eps"], L, 0 if rows_sharded else rank)
-    for i in range(args.warmup):
-        eng.hmc_step(th, hy, seed, i, eps, L, stats=stats)
+    n_warm = 0
+    while True:
+        eng.hmc_step(th, hy, seed, n_warm, eps, L, stats=stats)
+        n_warm += 1
+        acc_w = stats[:, 1].cpu().numpy()
+        if not args.no_tune:
+            eps = np.where(acc_w >= 0.5, eps, eps * 0.5)   # the chain moved into a stiffer region: keep adapting (untimed)
+        if n_warm >= args.warmup and (args.no_tune or np.mean(acc_w >= 0.5) >= 0.9 or n_warm >= args.warmup + 16):
+            break
     # ---------------- device-resident throughput ("value")
     clocks = ClockSampler(local_rank)
     barrier()
@@ -438,7 +445,7 @@ def main():
     for i in range(args.steps):
         flush.zero_()                                   # evict L2 between timed iterations
         evs[i][0].record()
-        eng.hmc_step(th, hy, seed, args.warmup + i, eps, L, stats=stats)
+        eng.hmc_step(th, hy, seed, n_warm + i, eps, L, stats=stats)
         evs[i][1].record()
     barrier()
     gpu_launches = eng.launches - launches0
@@ -541,7 +548,8 @@ def main():
             "data": "synthetic",
             "config": config_dict(cfg, L, cfg["eps"], world, rows_sharded),
             "step_size": {"nominal": float(cfg["eps"]), "median_used": float(np.median(eps)), "min_used": float(eps.min()),
-                          "how": "per-chain halving until a 10-step trajectory is accepted with probability >= 0.5"},
+                          "how": "per-chain halving until an L-step trajectory is accepted with probability >= 0.5, from the start state and "
+                                 "again after every (untimed) warm-up transition", "warmup_transitions": int(n_warm)},
             "us_per_leapfrog": 1e3 * dev_ms / (args.steps * L),
             "accept_prob_last": accept, "accepted_fraction_last": moved,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -93,8 +93,14 @@ def c2(N=9600, D=784, seed=21, teacher_seed=3):
     """docs/ClassificationExample.md stand-in: U[0,1)^{N x 784}, labels from a
     fixed random 784-20-20-1 teacher thresholded at its median."""
     rng = np.random.default_rng(seed)
-    X = rng.random((N, D))
-    t = _teacher(X - 0.5, [D, 20, 20, 1], teacher_seed)[:, 0]
+    if N * D > (1 << 27):
+        # C2-L (1,048,576 x 784): float32 draws and a chunked teacher keep the host footprint at 3.3 GB
+        X = rng.random((N, D), dtype=np.float32)
+        t = np.concatenate([_teacher(X[i:i + 65536].astype(np.float64) - 0.5, [D, 20, 20, 1], teacher_seed)[:, 0]
+                            for i in range(0, N, 65536)])
+    else:
+        X = rng.random((N, D))
+        t = _teacher(X - 0.5, [D, 20, 20, 1], teacher_seed)[:, 0]
     Y = (t > np.median(t)).astype(np.float64)
     arch = mlp_arch([D, 20, 20, 1], "dense", "relu", "sigmoid")
     return dict(name="C2", arch=arch, lik=("bernoulli",), X=X, Y=Y, eps=1e-3, L=500,
