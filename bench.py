@@ -294,7 +294,7 @@ def run_predictor(args, restore_stdout):
         flush.zero_()
         s_d, x_d = samples_h.cuda(non_blocking=True), X_h.cuda(non_blocking=True)
         _, mom = eng.predict(s_d, x_d, want_out=False, want_moments=True)
-        n, mu, m2 = parallel.merge_moments(mom[0], mom[1], mom[2])
+        n, mu, m2 = parallel.merge_moments_reduce(mom[0], mom[1], mom[2])     # one all-reduce of 3 x [out, M] float64
         out_h[0].copy_(mu, non_blocking=True)
         out_h[1].copy_((m2 / torch.clamp(n - 1, min=1)).sqrt(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -312,7 +312,7 @@ def run_predictor(args, restore_stdout):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3", "data": "synthetic",
                 "config": {"workload": "C5 slice", "samples_per_gpu": S_step, "test_rows": M, "network": "1-64-64-64-1",
-                           "mode": "fused per-row (count, mean, M2)", "parallelism": "samples split, one merge at the end",
+                           "mode": "fused per-row (count, mean, M2)", "parallelism": "samples split, one all-reduce of the per-row moments at the end",
                            "l2": "flushed between timed steps (256 MB write)"},
                 "e2e": {"value": e2e_value, "unit": "sample-rows/s", "h2d_bytes_per_step": int(samples_h.numel() * 4 + X_h.numel() * 4),
                         "d2h_bytes_per_step": int(out_h.numel() * 4), "steps": e2e_steps,

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "../../include/tbnn.h"
@@ -296,6 +297,10 @@ static int plan_predict(tbnn_handle* h) {
 }
 
 // ------------------------------------------------------------------ small kernels
+__global__ void k_widen(const float* src, double* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
 template <typename T> __global__ void k_cast_out(const double* src, T* dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (T)src[i];
@@ -838,13 +843,10 @@ extern "C" int tbnn_hyper_logp_grad(tbnn_handle* h, const void* theta, const voi
   const double* sse_d = nullptr;
   if (h->mp.lik == LIK_GAUSS) {
     if (sse) {
-      // caller-supplied statistic in dtype: widen to double
+      // caller-supplied statistic in dtype: widen to double on the device (no host round trip)
       if (h->dtype == TBNN_F32) {
-        std::vector<float> tmp(h->C);
-        CU(cudaMemcpyAsync(tmp.data(), sse, h->C * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        std::vector<double> d(tmp.begin(), tmp.end());
-        CU(cudaMemcpyAsync(h->sse_tmp(), d.data(), h->C * 8, cudaMemcpyHostToDevice, st));
+        k_widen<<<(h->C + 127) / 128, 128, 0, st>>>((const float*)sse, h->sse_tmp(), h->C);
+        h->launches++;
       } else {
         CU(cudaMemcpyAsync(h->sse_tmp(), sse, h->C * 8, cudaMemcpyDeviceToDevice, st));
       }
@@ -899,8 +901,21 @@ extern "C" int tbnn_adapter_ucb(int device, const float* eGrid, int eNumber, con
   CU(cudaSetDevice(device));
   const size_t fl = (size_t)eNumber + lNumber + 2 * n_hist + (size_t)n_hist * n_hist + n_hist + 4;
   const size_t wsb = adapter_workspace_bytes(eNumber, lNumber);
-  char* buf = nullptr;
-  CU(cudaMalloc(&buf, fl * sizeof(float) + wsb + 256));
+  // one device buffer per device, kept between calls (the adapter decides every few epochs: no cudaMalloc / cudaFree
+  // on the sampling path); a call is still synchronous -- its result steers the next epoch
+  static std::mutex mu;
+  static char* cache[64] = {};
+  static size_t cache_bytes[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  const size_t need = fl * sizeof(float) + wsb + 256;
+  if (device < 0 || device >= 64) return fail("bad device ordinal");
+  if (cache_bytes[device] < need) {
+    if (cache[device]) cudaFree(cache[device]);
+    cache[device] = nullptr; cache_bytes[device] = 0;
+    CU(cudaMalloc(&cache[device], need));
+    cache_bytes[device] = need;
+  }
+  char* buf = cache[device];
   std::vector<float> host(fl);
   size_t o = 0;
   const size_t oE = o; memcpy(&host[o], eGrid, eNumber * 4); o += eNumber;
@@ -919,7 +934,6 @@ extern "C" int tbnn_adapter_ucb(int device, const float* eGrid, int eNumber, con
   }
   float res[3] = {0, 0, 0};
   if (e == cudaSuccess) e = cudaMemcpy(res, d + oO, 3 * sizeof(float), cudaMemcpyDeviceToHost);
-  cudaFree(buf);
   if (e != cudaSuccess) return fail(std::string("adapter_ucb: ") + cudaGetErrorString(e));
   out_eL[0] = res[0]; out_eL[1] = res[1];
   if (out_ucb) *out_ucb = res[2];

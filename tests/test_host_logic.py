@@ -275,6 +275,13 @@ def _worker(rank, world, port, q):
     n, mu, s = parallel.merge_moments(cnt, mean, m2)
     ok = bool(torch.allclose(mu, torch.tensor(data.mean(axis=0))) and
               torch.allclose(s / n, torch.tensor(data.var(axis=0))) and torch.all(n == 11))
+    # the one-collective variant of the same merge (float64 sums, one all-reduce)
+    n2, mu2, s2 = parallel.merge_moments_reduce(cnt.float(), mean.float(), m2.float())
+    ok = ok and bool(torch.allclose(mu2.double(), mu, rtol=1e-6) and torch.allclose(s2.double(), s, rtol=1e-5)
+                     and torch.all(n2 == 11))
+    # chain split of the default bench workload: every chain exactly once (1,024 chains over the ranks)
+    owned = [(1024 * r // world, 1024 * (r + 1) // world) for r in range(world)]
+    ok = ok and owned[0][0] == 0 and owned[-1][1] == 1024 and all(owned[i][1] == owned[i + 1][0] for i in range(world - 1))
     # unique-id broadcast
     payload = bytes(range(128)) if rank == 0 else bytes(128)
     got = parallel.broadcast_bytes(payload, 0)
