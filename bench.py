@@ -288,16 +288,22 @@ def run_predictor(args, restore_stdout):
     # end to end: samples and test rows from pinned host memory, merged mean / sd back to the host
     out_h = torch.empty(2, mom.shape[1], M, dtype=torch.float32).pin_memory()
     e2e_steps = max(2, args.steps // 2)
+    merge = parallel.merge_moments if args.pred_merge == "gather" else parallel.merge_moments_reduce
+
+    def e2e_step():
+        s_d, x_d = samples_h.cuda(non_blocking=True), X_h.cuda(non_blocking=True)
+        _, mom = eng.predict(s_d, x_d, want_out=False, want_moments=True)
+        n, mu, m2 = merge(mom[0], mom[1], mom[2])
+        out_h[0].copy_(mu, non_blocking=True)
+        out_h[1].copy_((m2 / torch.clamp(n - 1, min=1)).sqrt(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()                                          # untimed: first use of the merge collective sets up its channels
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         flush.zero_()
-        s_d, x_d = samples_h.cuda(non_blocking=True), X_h.cuda(non_blocking=True)
-        _, mom = eng.predict(s_d, x_d, want_out=False, want_moments=True)
-        n, mu, m2 = parallel.merge_moments_reduce(mom[0], mom[1], mom[2])     # one all-reduce of 3 x [out, M] float64
-        out_h[0].copy_(mu, non_blocking=True)
-        out_h[1].copy_((m2 / torch.clamp(n - 1, min=1)).sqrt(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.dev)
@@ -376,6 +382,7 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="TBNN_FLAG_* for the engine (64 = FFMA tile engine instead of tcgen05)")
     ap.add_argument("--pred-samples", type=int, default=512, help="c5: stored samples per GPU and step")
     ap.add_argument("--pred-rows", type=int, default=1048576, help="c5: test rows")
+    ap.add_argument("--pred-merge", default="reduce", help="c5 end-to-end moment merge: reduce (one float64 all-reduce) | gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
