@@ -311,7 +311,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         const uint32_t dbig = umma::tmem_addr(tbase, 0, acc == 0 ? col_big(ti) : col_w(ti));
         const uint32_t dsml = split ? umma::tmem_addr(tbase, 0, col_small(ti)) : dbig;
         const uint32_t halfB = 8u * cgsB;
-        for (int ch = 0; ch < nch; ++ch, ++cc) {
+        auto chunk = [&](int ch) {
           const uint32_t st = cc % TU_NS, use = cc / TU_NS;
           mbar_wait(&bars->fullA[st], use & 1u);         // one thread: spinning is cheap and wakes up at once
           mbar_wait(&bars->fullB[st], use & 1u);
@@ -344,6 +344,12 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           }
           umma::commit(&bars->emptyA[st]);
           umma::commit(&bars->emptyB[st]);
+        };
+        if (HW == 128) {
+#pragma unroll 1
+          for (int ch = 0; ch < nch; ++ch, ++cc) chunk(ch);
+        } else {
+          for (int ch = 0; ch < nch; ++ch, ++cc) chunk(ch);
         }
         umma::commit(&bars->accfull[bi]);
         TU_MARK(1, prof_k, ti, 2 + 8 * acc);
@@ -357,7 +363,16 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           for (int k = 0; k < 2 * G; ++k) {
             for (int ti = 0; ti < ntl; ++ti) {
               prof_k = k;
-              if (k == 0) gemm(ti, tp.nK0, ks0, idF, tu_cgs(HW), 0, true);
+              if (HW == 128) {
+                // One call site per accumulator and a rolled chunk loop: the 128-wide kernel is held back by instruction
+                // fetch (210 KB of SASS per variant, instruction-cache hit rate 81 %): 11.87 -> 11.40 ms at C4.  The
+                // 64-wide kernel is bound by how fast this one thread issues: there the unrolled form below is 8 % faster
+                // (5.58 vs 6.03 ms at C3), and running the issuer warp-wide with an elected lane is slower still
+                // (profiles/r2h_summary.md).
+                const int l = 2 * G - 1 - k;                 // backward segments: block whose dZ was just produced
+                if (k < G || l >= 1) gemm(ti, k == 0 ? tp.nK0 : nH, k == 0 ? ks0 : 4, idF, tu_cgs(HW), 0, k < G);   // F_k or B_l
+                if (k >= G) gemm(ti, 4, 4, l >= 1 ? idWh : idW0, l >= 1 ? tu_cgs(NWH) : tu_cgs(tp.N0w), 1, false);  // W_l
+              } else if (k == 0) gemm(ti, tp.nK0, ks0, idF, tu_cgs(HW), 0, true);
               else if (k < G) gemm(ti, nH, 4, idF, tu_cgs(HW), 0, true);
               else {
                 const int l = 2 * G - 1 - k;
