@@ -154,7 +154,7 @@ __device__ __forceinline__ void put_row_chunk(uint32_t stage, int r, const float
   for (int kq = 0; kq < 8; ++kq) {
     float h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) umma::split_tf32_fast(v[4 * kq + i], h[i], l[i]);
+    for (int i = 0; i < 4; ++i) umma::split_tf32_rn_exact(v[4 * kq + i], h[i], l[i]);
     const uint32_t a = stage + kq * TU_CGA + r * 16;
     sts128(a, h[0], h[1], h[2], h[3]);
     sts128(a + TU_HALFA, l[0], l[1], l[2], l[3]);
@@ -163,10 +163,23 @@ __device__ __forceinline__ void put_row_chunk(uint32_t stage, int r, const float
 // one value of the transposed (K = rows) operand: operand row n, k = lane, column-group stride cgs
 __device__ __forceinline__ void put_t(uint32_t stage, int half, int cgs, int n, int lane, float v) {
   float h, l;
-  umma::split_tf32_fast(v, h, l);
+  umma::split_tf32_rn_exact(v, h, l);
   const uint32_t a = stage + (n >> 3) * 128 + (lane >> 2) * cgs + (n & 7) * 16 + (lane & 3) * 4;
   sts32(a, h);
   sts32(a + half, l);
+}
+// The same with the lane- and column-base-dependent part of the address hoisted: tb = put_t_base(stage, cgs, n0, lane)
+// for a column base n0 that is a multiple of 8; operand row n0 + j with a COMPILE-TIME j is then a store at an
+// immediate offset (the address arithmetic of put_t was 11 % of all executed instructions of the 64-wide kernel)
+__device__ __forceinline__ uint32_t put_t_base(uint32_t stage, int cgs, int n0, int lane) {
+  return stage + (n0 >> 3) * 128 + (lane >> 2) * cgs + (lane & 3) * 4;
+}
+__device__ __forceinline__ void put_t_at(uint32_t tb_hi, uint32_t tb_lo, int j, float v) {
+  float h, l;
+  umma::split_tf32_rn_exact(v, h, l);
+  const uint32_t off = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
+  sts32(tb_hi + off, h);
+  sts32(tb_lo + off, l);
 }
 
 // Optional clock64 timeline of CTA 0 (build with -DTBNN_TU_PROFILE; read with tbnn_tu_profile): (tag, clock) pairs of
@@ -474,16 +487,18 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         const uint32_t st = slot(cc + q);
         if (q == wq) {
           const uint32_t sa = ringA + st * TU_ASTAGE, sb = ringB + st * tp.b_stage;
+          const uint32_t ta = put_t_base(sa, TU_CGA, cb, lane);
 #pragma unroll
-          for (int j = 0; j < HH; ++j) put_t(sa, TU_HALFA, TU_CGA, cb + j, lane, dz[j]);
+          for (int j = 0; j < HH; ++j) put_t_at(ta, ta + TU_HALFA, j, dz[j]);
           if (HW == 64) {
 #pragma unroll
-            for (int j = 0; j < HH; ++j) put_t(sa, TU_HALFA, TU_CGA, 64 + cb + j, lane, STACKQ ? qv[STACKQ ? j : 0] : 0.f);
+            for (int j = 0; j < HH; ++j) put_t_at(ta + 8 * 128, ta + 8 * 128 + TU_HALFA, j, STACKQ ? qv[STACKQ ? j : 0] : 0.f);
           }
           if (l >= 1) {
             const int cgs = tu_cgs(NWH), half = tu_half(NWH);
             const float* sc = scr + (size_t)(l - 1) * HW * 128;
             const float* sl = slope_s + (l - 1) * HW + cb;
+            const uint32_t tbb = put_t_base(sb, cgs, cb, lane);
             float4 kv[HH / 4];
 #pragma unroll
             for (int g4 = 0; g4 < HH / 4; ++g4) kv[g4] = *reinterpret_cast<const float4*>(sc + ((size_t)(cb / 4 + g4) * 128 + r) * 4);
@@ -492,7 +507,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
               const float k4[4] = {kv[g4].x, kv[g4].y, kv[g4].z, kv[g4].w};
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                put_t(sb, half, cgs, cb + 4 * g4 + i, lane, tu_from_keep<ACTK>(hact, k4[i], SLOPES ? sl[4 * g4 + i] : 0.f));
+                put_t_at(tbb, tbb + half, 4 * g4 + i, tu_from_keep<ACTK>(hact, k4[i], SLOPES ? sl[4 * g4 + i] : 0.f));
             }
             if (grp == 1) put_t(sb, half, cgs, HW, lane, 1.f);
           } else if (grp == 0) {
@@ -566,7 +581,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
                     for (int i = 0; i < 4; ++i) {
                       const int kk = 32 * ch + 4 * kq + i;
                       const float x = (valid && kk < D) ? xrow[kk] : 0.f;
-                      umma::split_tf32_fast(x, h[i], l4[i]);
+                      umma::split_tf32_rn_exact(x, h[i], l4[i]);
                     }
                     const uint32_t a = stage + kq * TU_CGA + r * 16;
                     sts128(a, h[0], h[1], h[2], h[3]);

@@ -143,6 +143,14 @@ __device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
   lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
 }
 
+// Three-instruction split for the row workers of the training sweep: hi rounded to nearest as above, lo = x - hi left
+// as the exact fp32 remainder -- the tensor core truncates it to TF32.  Because hi is rounded to NEAREST, lo has either
+// sign, so its truncation (toward zero, <= 2^-21 |x|) does not pile up one-sidedly the way a truncated hi does.
+__device__ __forceinline__ void split_tf32_rn_exact(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
 // cheaper split for forward-only use (posterior-predictive sweep): hi = truncation (what the tensor core does to
 // its operands anyway), lo = exact remainder, truncated again by the hardware -> one-sided error ~2^-21 |x| per
 // product, irrelevant next to Monte Carlo error; two ALU instructions instead of two conversions and a subtract
