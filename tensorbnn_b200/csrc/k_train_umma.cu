@@ -35,8 +35,11 @@
 
 namespace tbnn {
 
-constexpr int TU_THREADS = 320;          // warps 0-7 row workers, warp 8 MMA issuer (+ TMEM alloc), warp 9 TMA producer
-constexpr int TU_MMA_WARP = 8, TU_TMA_WARP = 9;
+// TPR threads share a training row (each owns HW / TPR columns): 4 TPR row-worker warps, then the MMA issuer warp
+// (+ TMEM alloc) and the TMA producer warp.  TPR = 2: 320 threads, 168 registers.  TPR = 4 (64-wide networks): 576
+// threads, 16 columns per thread, 112 registers -- four row-worker warps per scheduler instead of two hide the
+// dependent-issue latency this kernel is bound by (profiles/r2h_summary.md).
+__host__ __device__ constexpr int tu_threads(int tpr) { return 32 * (4 * tpr + 2); }
 constexpr int TU_NS_MAX = 4;                   // ring stages: 4 for the 64-wide network (all four chunks of a weight-gradient GEMM
                                                // in flight at once), 3 for the 128-wide one (shared memory)
 __host__ __device__ constexpr int tu_ns(int hw) { return hw == 64 ? 4 : 3; }
@@ -47,7 +50,7 @@ constexpr int TU_ASTAGE = 2 * TU_HALFA;
 __host__ __device__ constexpr int tu_cgs(int rows) { return 128 * (rows / 8) + 16; }
 __host__ __device__ constexpr int tu_half(int rows) { return 8 * tu_cgs(rows); }
 
-__device__ __forceinline__ void ew_barrier() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+template <int NTHR> __device__ __forceinline__ void ew_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(NTHR) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
@@ -72,6 +75,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) { v[i] = a[i]; v[16 + i] = b[i]; }
 }
+
+// 16 accumulator columns
+__device__ __forceinline__ void tmem_ld16w(uint32_t taddr, float (&v)[16]) {
+  umma::tmem_ld16(taddr, v);
+  umma::tmem_ld_wait();
+}
+// column sums of 16 values per lane over the 32 lanes of a warp: on return every lane holds the sum of column
+// colsum16_col(lane) (16 shuffles; lanes 2i and 2i + 1 hold the same column)
+__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool up = (lane & (2 * s)) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * s);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int colsum16_col(int lane) { return lane >> 1; }
 
 // column sums over the 32 lanes of a warp: on return lane i holds sum over lanes of v[i] (31 shuffles)
 __device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
@@ -148,14 +173,16 @@ template <int ACTK> __device__ __forceinline__ float tu_deriv(int act, float s, 
   return act_deriv_from_out<float>(act, s);
 }
 
-// this thread's row as a K-major operand chunk of 32 features: 8 column groups, hi and lo halves
-__device__ __forceinline__ void put_row_chunk(uint32_t stage, int r, const float* v) {
+// NCG column groups (4 features each, hi and lo halves), starting at group kq0, of this thread's row of a K-major
+// operand chunk of 32 features
+template <int NCG>
+__device__ __forceinline__ void put_row_part(uint32_t stage, int r, int kq0, const float* v) {
 #pragma unroll
-  for (int kq = 0; kq < 8; ++kq) {
+  for (int kq = 0; kq < NCG; ++kq) {
     float h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) umma::split_tf32_rn_exact(v[4 * kq + i], h[i], l[i]);
-    const uint32_t a = stage + kq * TU_CGA + r * 16;
+    const uint32_t a = stage + (kq0 + kq) * TU_CGA + r * 16;
     sts128(a, h[0], h[1], h[2], h[3]);
     sts128(a + TU_HALFA, l[0], l[1], l[2], l[3]);
   }
@@ -208,9 +235,10 @@ struct TuBars {
 // memory holds two tiles' accumulators only for the 64-wide network.
 template <int HW> struct TuTiles { static constexpr int value = HW == 64 ? 2 : 1; };
 
-// 168 registers per thread: register allocation rounds the 10 warps up to 12 (a launch with 200 is refused)
-template <int HW, int ACTK>
-__global__ void __launch_bounds__(TU_THREADS, 1)
+// TPR = 2: 168 registers per thread (register allocation rounds the 10 warps up to 12; a launch with 200 is refused);
+// TPR = 4: 112
+template <int HW, int ACTK, int TPR>
+__global__ void __launch_bounds__(tu_threads(TPR), 1)
 k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ TrainUmmaPlan tp, int C, int S,
              const float* __restrict__ theta_pad, const unsigned char* __restrict__ wimg,
              const float* __restrict__ X, const float* __restrict__ Y, long long N, float* __restrict__ partial,
@@ -220,8 +248,11 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
   constexpr int NT = TuTiles<HW>::value;        // tiles in flight
   constexpr int TU_NS = tu_ns(HW);              // ring stages
   constexpr int nH = HW / 32;                   // chunks of a hidden-width contraction
-  constexpr int HH = HW / 2;                    // columns per row worker (two threads share a row)
-  constexpr int nHH = HH / 32;                  // chunks per column group
+  constexpr int RWT = 128 * TPR;                // row-worker threads
+  constexpr int TU_MMA_WARP = 4 * TPR, TU_TMA_WARP = 4 * TPR + 1;
+  constexpr int HH = HW / TPR;                  // columns per row worker (TPR threads share a row)
+  constexpr int nP = HH / 16;                   // 16-column pieces per row worker
+  static_assert(HH == 16 || HH == 32 || HH == 64, "columns per row worker");
   constexpr int NWH = HW + 16;                  // N of a hidden weight-gradient GEMM: [A | 1 | pad]
   constexpr bool SLOPES = ACTK == ACT_SQPRELU;
   constexpr bool STACKQ = SLOPES && HW == 64;   // slope gradients ride in operand rows 64..127
@@ -231,18 +262,23 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
   float* par = reinterpret_cast<float*>(smraw + tp.off_par);
   const uint32_t ringA = smem_u32(smraw + tp.off_a), ringB = smem_u32(smraw + tp.off_b);
   const long long ntile = (N + 127) >> 7;
+  // Tiles of work item s of a chain: [s * tbase + min(s, trem), +tbase + (s < trem)) with tbase = ntile / S, trem = ntile % S
+  // computed ONCE -- a 64-bit division per item is a subroutine call whose result the compiler treats as thread-varying,
+  // which drags the MMA issuer's ring counter and every descriptor derived from it off the uniform datapath.
+  const long long tile_base = ntile / S;
+  const int tile_rem = (int)(ntile - tile_base * S);
   const int nitem = C * S;
 
   if (tid == 0) {
     for (int i = 0; i < TU_NS; ++i) {
-      mbar_init(&bars->fullA[i], 8);
+      mbar_init(&bars->fullA[i], 4 * TPR);
       mbar_init(&bars->emptyA[i], 1);
-      mbar_init(&bars->fullB[i], 2);
+      mbar_init(&bars->fullB[i], TPR);          // a weight-gradient chunk is written by the TPR warps of one lane quarter
       mbar_init(&bars->emptyB[i], 1);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->accfull[i], 1);
-      mbar_init(&bars->accfree[i], 8);
+      mbar_init(&bars->accfree[i], 4 * TPR);
     }
     mbar_fence_init();
   }
@@ -278,14 +314,14 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       auto load = [&](const unsigned char* src) {
         const uint32_t st = cc % TU_NS, use = cc / TU_NS;
         mbar_wait_parked(&bars->emptyB[st], (use & 1u) ^ 1u);
-        mbar_expect_tx(&bars->fullB[st], cbytes);
-        mbar_arrive(&bars->fullB[st]);
+        mbar_expect_tx(&bars->fullB[st], cbytes);        // one arrival ...
+        mbar_arrive_n(&bars->fullB[st], TPR - 1);        // ... and the rest of the count
         bulk_g2s(smraw + tp.off_b + st * tp.b_stage, src, cbytes, &bars->fullB[st]);
         ++cc;
       };
       for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
         const int c = item / S, s = item - c * S;
-        const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
+        const long long t0 = s * tile_base + (s < tile_rem ? s : tile_rem), t1 = t0 + tile_base + (s < tile_rem ? 1 : 0);
         const unsigned char* img = wimg + (size_t)c * tp.wimg_chain;
         for (long long tb = t0; tb < t1; tb += NT) {
           const int ntl = NT == 1 ? 1 : (int)((t1 - tb) < NT ? (t1 - tb) : NT);
@@ -308,7 +344,10 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
   } else if (warp == TU_MMA_WARP) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      uint32_t cc = 0, accuse[4] = {0u, 0u, 0u, 0u};
+      // accpar: bit bi = parity of the number of uses of accumulator region bi.  (A dynamically indexed counter array
+      // lives in local memory; the spin wait on a parity loaded from there made the compiler treat everything after
+      // it as thread-varying -- ring counter, descriptors -- and wrap every MMA in an R2UR waterfall.)
+      uint32_t cc = 0, accpar = 0u;
       const uint32_t idF = umma::idesc_tf32(128, HW, false, false);
       const uint32_t idWh = umma::idesc_tf32(128, NWH, false, false);
       const uint32_t idW0 = umma::idesc_tf32(128, tp.N0w, false, false);
@@ -318,8 +357,8 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       auto gemm = [&](int ti, int nch, int ks_last, uint32_t idesc, int cgsB, int acc, bool split) {
         const int bi = 2 * ti + acc;
         TU_MARK(1, prof_k, ti, 0 + 8 * acc);
-        mbar_wait(&bars->accfree[bi], (accuse[bi] & 1u) ^ 1u);
-        accuse[bi]++;
+        mbar_wait(&bars->accfree[bi], ((accpar >> bi) & 1u) ^ 1u);
+        accpar ^= 1u << bi;
         umma::fence_after_sync();
         const uint32_t dbig = umma::tmem_addr(tbase, 0, acc == 0 ? col_big(ti) : col_w(ti));
         const uint32_t dsml = split ? umma::tmem_addr(tbase, 0, col_small(ti)) : dbig;
@@ -332,28 +371,18 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           if (ch == 0) TU_MARK(1, prof_k, ti, 1 + 8 * acc);
           const uint32_t a0 = ringA + st * TU_ASTAGE, b0 = ringB + st * tp.b_stage;
           const int ks = ch == nch - 1 ? ks_last : 4;
-          // descriptors of k step 0; a k step advances the start-address field (bytes >> 4) by two column groups
-          const uint64_t dAh0 = umma::smem_desc(a0, TU_CGA, 128u), dAl0 = umma::smem_desc(a0 + TU_HALFA, TU_CGA, 128u);
-          const uint64_t dBh0 = umma::smem_desc(b0, cgsB, 128u), dBl0 = umma::smem_desc(b0 + halfB, cgsB, 128u);
-          const uint64_t stepA = (uint64_t)((2 * TU_CGA) >> 4), stepB = (uint64_t)((2 * cgsB) >> 4);
+          // descriptors as 32-bit words (umma::mma_tf32_ss32: they stay in uniform registers); a k step advances the
+          // start-address field (bytes >> 4) of the lo word by two column groups
+          const uint32_t hiw = umma::desc_hi(128u);
+          const uint32_t aH0 = umma::desc_lo(a0, TU_CGA), aL0 = umma::desc_lo(a0 + TU_HALFA, TU_CGA);
+          const uint32_t bH0 = umma::desc_lo(b0, cgsB), bL0 = umma::desc_lo(b0 + halfB, cgsB);
+          const uint32_t stepA = (uint32_t)((2 * TU_CGA) >> 4), stepB = (uint32_t)((2 * cgsB) >> 4);
           for (int k = 0; k < ks; ++k) {
-            // Two ways to the same descriptors; which one issues faster was MEASURED per width (the small-N MMAs of the
-            // 64-wide network are issue-bound: 5.77 -> 5.57 ms with the incremental form; the 128-wide kernel lost 9 %
-            // with it -- the kernel is sensitive to its own code size and layout)
-            uint64_t dAh, dAl, dBh, dBl;
-            if (HW == 64) {
-              dAh = dAh0 + k * stepA; dAl = dAl0 + k * stepA;
-              dBh = dBh0 + k * stepB; dBl = dBl0 + k * stepB;
-            } else {
-              dAh = umma::smem_desc(a0 + k * 2 * TU_CGA, TU_CGA, 128u);
-              dAl = umma::smem_desc(a0 + TU_HALFA + k * 2 * TU_CGA, TU_CGA, 128u);
-              dBh = umma::smem_desc(b0 + k * 2 * cgsB, cgsB, 128u);
-              dBl = umma::smem_desc(b0 + halfB + k * 2 * cgsB, cgsB, 128u);
-            }
+            const uint32_t aH = aH0 + k * stepA, aL = aL0 + k * stepA, bH = bH0 + k * stepB, bL = bL0 + k * stepB;
             const bool first = ch == 0 && k == 0;
-            umma::mma_tf32_ss(dsml, dAl, dBh, idesc, !first);
-            umma::mma_tf32_ss(dsml, dAh, dBl, idesc, true);
-            umma::mma_tf32_ss(dbig, dAh, dBh, idesc, split ? !first : true);
+            umma::mma_tf32_ss32(dsml, aL, hiw, bH, hiw, idesc, !first);
+            umma::mma_tf32_ss32(dsml, aH, hiw, bL, hiw, idesc, true);
+            umma::mma_tf32_ss32(dbig, aH, hiw, bH, hiw, idesc, split ? !first : true);
           }
           umma::commit(&bars->emptyA[st]);
           umma::commit(&bars->emptyB[st]);
@@ -370,7 +399,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       const int ks0 = (tp.K0p - 32 * (tp.nK0 - 1)) / 8;
       for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
         const int s = item % S;
-        const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
+        const long long t0 = s * tile_base + (s < tile_rem ? s : tile_rem), t1 = t0 + tile_base + (s < tile_rem ? 1 : 0);
         for (long long tb = t0; tb < t1; tb += NT) {
           const int ntl = NT == 1 ? 1 : (int)((t1 - tb) < NT ? (t1 - tb) : NT);
           for (int k = 0; k < 2 * G; ++k) {
@@ -404,7 +433,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
     const int r = 32 * wq + lane;                        // row of the tile = TMEM lane
     const int cb = grp * HH;                             // first column of this thread
     const uint32_t lane_t = (uint32_t)(32 * wq) << 16;
-    uint32_t cc = 0, accuse[4] = {0u, 0u, 0u, 0u};
+    uint32_t cc = 0, accpar = 0u;                        // bit bi = parity of the uses of accumulator region bi
     float* bias_s = par + tp.par_bias;                   // [G][HW]
     float* slope_s = par + tp.par_slope;                 // [G][HW] effective negative-side slope
     float* sfac_s = par + tp.par_sraw;                   // [G][HW] d(effective slope)/d(parameter): 2 s or 1
@@ -417,8 +446,8 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
 
     auto wait_acc = [&](int ti, int a) {
       const int bi = 2 * ti + a;
-      mbar_wait_parked(&bars->accfull[bi], accuse[bi] & 1u);
-      accuse[bi]++;
+      mbar_wait_parked(&bars->accfull[bi], (accpar >> bi) & 1u);
+      accpar ^= 1u << bi;
       umma::fence_after_sync();
     };
     auto free_acc = [&](int ti, int a) {                  // this warp has read its share of that accumulator region
@@ -445,8 +474,15 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
 #pragma unroll
       for (int jj = 0; jj < nH; ++jj) {
         const uint32_t st = slot(cc + jj);
-        if (jj / nHH == grp) put_row_chunk(ringA + st * TU_ASTAGE, r, v + 32 * (jj % nHH));
-        done(st, jj / nHH == grp);
+        bool own;
+        if (HH >= 32) {
+          own = jj / (HH / 32) == grp;
+          if (own) put_row_part<8>(ringA + st * TU_ASTAGE, r, 0, v + (HH >= 32 ? 32 * (jj % (HH / 32)) : 0));
+        } else {                                           // 16 columns: half a chunk
+          own = jj == (grp >> 1);
+          if (own) put_row_part<4>(ringA + st * TU_ASTAGE, r, (grp & 1) * 4, v);
+        }
+        done(st, own);
       }
       cc += nH;
     };
@@ -466,7 +502,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           for (int i = 0; i < 16; i += 4) red_add4(gw + n0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
-      if (grp == 1) {
+      if (grp == TPR - 1) {
         float v[8];
         umma::tmem_ld8(tbase + lane_t + col_w(ti) + HW, v);
         umma::tmem_ld_wait();
@@ -509,7 +545,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
               for (int i = 0; i < 4; ++i)
                 put_t_at(tbb, tbb + half, 4 * g4 + i, tu_from_keep<ACTK>(hact, k4[i], SLOPES ? sl[4 * g4 + i] : 0.f));
             }
-            if (grp == 1) put_t(sb, half, cgs, HW, lane, 1.f);
+            if (grp == TPR - 1) put_t(sb, half, cgs, HW, lane, 1.f);
           } else if (grp == 0) {
             const int cgs = tu_cgs(tp.N0w), half = tu_half(tp.N0w);
             for (int k = 0; k < D; ++k) put_t(sb, half, cgs, k, lane, valid ? xrow[k] : 0.f);
@@ -526,11 +562,11 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
 
     for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
       const int c = item / S, s = item - c * S;
-      const long long t0 = ntile * s / S, t1 = ntile * (s + 1) / S;
+      const long long t0 = s * tile_base + (s < tile_rem ? s : tile_rem), t1 = t0 + tile_base + (s < tile_rem ? 1 : 0);
       const float* th = theta_pad + (size_t)c * mp.Ppad;
       gout = partial + ((size_t)c * S + s) * mp.Ppad;
-      ew_barrier();                                      // previous item's parameters are dead
-      for (int e = tid; e < G * HW; e += 256) {
+      ew_barrier<RWT>();                                      // previous item's parameters are dead
+      for (int e = tid; e < G * HW; e += RWT) {
         const int l = e / HW, j = e - l * HW;
         const BlockPlan& b = mp.b[l];
         bias_s[e] = th[b.pb + j];
@@ -541,7 +577,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         slope_s[e] = sl;
         sfac_s[e] = fac;
       }
-      for (int e = tid; e < OUT * HW + 4; e += 256) {
+      for (int e = tid; e < OUT * HW + 4; e += RWT) {
         float v = 0.f;
         if (e < OUT * HW) { const int o = e / HW, k = e - o * HW; v = th[bL.pw + o * bL.ld_in + k]; }
         else if (e - OUT * HW < OUT) v = th[bL.pb + e - OUT * HW];
@@ -549,9 +585,9 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
 #pragma unroll
         for (int w = 0; w < 4; ++w) par[tp.par_accl + w * (OUT * HW + 4) + e] = 0.f;
       }
-      for (int i = 4 * tid; i < mp.Ppad; i += 4 * 256) *reinterpret_cast<float4*>(gout + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 4 * tid; i < mp.Ppad; i += 4 * RWT) *reinterpret_cast<float4*>(gout + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       __threadfence();
-      ew_barrier();
+      ew_barrier<RWT>();
       stat = 0.0;
 
       for (long long tb = t0; tb < t1; tb += NT) {
@@ -603,12 +639,13 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
               wait_acc(ti, 0);
               if (tid == 0) TU_MARK(0, k, ti, 1);
 #pragma unroll
-              for (int j = 0; j < nHH; ++j) {
-                float vb[32], vs[32];
-                tmem_ld32(tbase + lane_t + col_big(ti) + cb + 32 * j, vb);
-                tmem_ld32(tbase + lane_t + col_small(ti) + cb + 32 * j, vs);
+              for (int j = 0; j < nP; ++j) {
+                float vb[16], vs[16];
+                umma::tmem_ld16(tbase + lane_t + col_big(ti) + cb + 16 * j, vb);
+                umma::tmem_ld16(tbase + lane_t + col_small(ti) + cb + 16 * j, vs);
+                umma::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dz[32 * j + i] = vb[i] + vs[i];
+                for (int i = 0; i < 16; ++i) dz[16 * j + i] = vb[i] + vs[i];
               }
               free_acc(ti, 0);
               const float* bz = bias_s + l * HW + cb;
@@ -631,7 +668,8 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
                 put_chunks(dz);
               } else {
                 // ---------------------------------------------- last hidden block, last block, likelihood
-                float* fx_s = par + tp.par_fx + ti * (2 * 128 * 4);
+                const int FXS = tp.fx_stride;
+                float* fx_s = par + tp.par_fx + ti * (TPR * 128 * FXS);
                 float f[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int col = 0; col < HH; ++col) {
@@ -642,14 +680,19 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
                   for (int o = 0; o < 4; ++o)
                     if (o < OUT) f[o] = fmaf(wl_s[o * HW + cb + col], a, f[o]);
                 }
-                *reinterpret_cast<float4*>(fx_s + (grp * 128 + r) * 4) = make_float4(f[0], f[1], f[2], f[3]);
-                ew_barrier();
-                {
-                  const float4 o4 = *reinterpret_cast<const float4*>(fx_s + ((grp ^ 1) * 128 + r) * 4);
-                  // fixed order (group 0 + group 1) so both threads of a row get identical bits
-                  const float4 m4 = make_float4(f[0], f[1], f[2], f[3]);
-                  const float4 a4 = grp == 0 ? m4 : o4, b4 = grp == 0 ? o4 : m4;
-                  f[0] = a4.x + b4.x; f[1] = a4.y + b4.y; f[2] = a4.z + b4.z; f[3] = a4.w + b4.w;
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                  if (o < OUT) fx_s[(grp * 128 + r) * FXS + o] = f[o];
+                ew_barrier<RWT>();
+                // fixed order (group 0 + group 1 + ...) so all threads of a row get identical bits
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                  if (o < OUT) {
+                    float acc = fx_s[r * FXS + o];
+#pragma unroll
+                    for (int g = 1; g < TPR; ++g) acc += fx_s[(g * 128 + r) * FXS + o];
+                    f[o] = acc;
+                  }
                 }
                 float dfl[4] = {0.f, 0.f, 0.f, 0.f};
                 const float lo = 1e-8f, hi = (float)(1 - 1e-7);          // likelihood.py:229-230
@@ -675,15 +718,24 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
                 }
                 // gradient of the last block (column sums over the tile's rows), dA_{G-1}, dZ_{G-1}
 #pragma unroll
-                for (int g = 0; g < nHH; ++g) {
+                for (int g = 0; g < (HH >= 32 ? HH / 32 : 1); ++g) {
 #pragma unroll
                   for (int o = 0; o < 4; ++o) {
                     if (o < OUT) {
-                      float pr[32];
+                      if (HH >= 32) {
+                        float pr[32];
 #pragma unroll
-                      for (int i = 0; i < 32; ++i) pr[i] = dfl[o] * tu_from_keep<ACTK>(hact, dz[32 * g + i], SLOPES ? sl[32 * g + i] : 0.f);
-                      const float cs = colsum32(pr, lane);
-                      accl_s[o * HW + cb + 32 * g + lane] += cs;
+                        for (int i = 0; i < 32; ++i)
+                          pr[i] = dfl[o] * tu_from_keep<ACTK>(hact, dz[(HH >= 32 ? 32 * g : 0) + i], SLOPES ? sl[(HH >= 32 ? 32 * g : 0) + i] : 0.f);
+                        const float cs = colsum32(pr, lane);
+                        accl_s[o * HW + cb + 32 * g + lane] += cs;
+                      } else {
+                        float pr[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pr[i] = dfl[o] * tu_from_keep<ACTK>(hact, dz[i], SLOPES ? sl[i] : 0.f);
+                        const float cs = colsum16(pr, lane);
+                        if ((lane & 1) == 0) accl_s[o * HW + cb + colsum16_col(lane)] += cs;
+                      }
                     }
                   }
                 }
@@ -722,11 +774,11 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
               wait_acc(ti, 0);
               if (tid == 0) TU_MARK(0, k, ti, 1);
 #pragma unroll
-              for (int j = 0; j < nHH; ++j) {
-                float v[32];
-                tmem_ld32(tbase + lane_t + col_big(ti) + cb + 32 * j, v);
+              for (int j = 0; j < nP; ++j) {
+                float v[16];
+                tmem_ld16w(tbase + lane_t + col_big(ti) + cb + 16 * j, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dz[32 * j + i] = v[i];
+                for (int i = 0; i < 16; ++i) dz[16 * j + i] = v[i];
               }
               free_acc(ti, 0);
 #pragma unroll
@@ -778,11 +830,11 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         }
       }
       // ---------------------------------------------------- item epilogue: last block gradient, statistic
-      ew_barrier();
+      ew_barrier<RWT>();
       {
         const float* a0 = par + tp.par_accl;
         const int ws = OUT * HW + 4;
-        for (int e = tid; e < OUT * HW; e += 256) {
+        for (int e = tid; e < OUT * HW; e += RWT) {
           const int o = e / HW, k = e - o * HW;
           gout[bL.pw + o * bL.ld_in + k] = ((a0[e] + a0[ws + e]) + a0[2 * ws + e]) + a0[3 * ws + e];
         }
@@ -795,7 +847,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         double* red = reinterpret_cast<double*>(par + tp.par_accl + 4 * (OUT * HW + 4));
         const double w = warp_sum(stat);
         if (lane == 0 && grp == 0) red[wq] = w;
-        ew_barrier();
+        ew_barrier<RWT>();
         if (tid == 0) stat_part[(size_t)c * S + s] = ((red[0] + red[1]) + red[2]) + red[3];
       }
     }
@@ -847,7 +899,16 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   tp.par_sraw = pf; pf += G * HW;
   tp.par_wl = pf; pf += mp.OUT * HW + 4;
   tp.par_accl = pf; pf += 4 * (mp.OUT * HW + 4) + 16;    // one per lane quarter, + 8 doubles of reduction scratch
-  tp.par_fx = pf; pf += 2 * 2 * 128 * 4;                 // [tile slot][column group][row][4]
+  // Four threads per row for the 64-wide network when the exchange buffer of the last block still fits; TBNN_TU_TPR=2
+  // in the environment keeps two (A/B measurements).
+  tp.fx_stride = mp.OUT == 1 ? 1 : (mp.OUT == 2 ? 2 : 4);
+  tp.par_fx = pf;
+  const char* env = getenv("TBNN_TU_TPR");
+  const int want = env ? atoi(env) : 0;
+  const int rest = tu_pad((int)sizeof(TuBars), 16) + 16;
+  tp.TPR = 2;
+  if (HW == 64 && want != 2 && (size_t)(off + (pf + 2 * 4 * 128 * tp.fx_stride) * 4 + rest) <= smem_limit) tp.TPR = 4;
+  pf += 2 * tp.TPR * 128 * tp.fx_stride;                 // [tile slot][column group][row][fx_stride]
   off += pf * 4;
   off = tu_pad(off, 16);
   tp.off_bar = off; off += (int)sizeof(TuBars);
@@ -884,20 +945,24 @@ void launch_train_umma(const ModelPlan& mp, const TrainUmmaPlan& tp, int num_sms
   k_train_prep<<<dim3((groups + 255) / 256, C), 256, 0, st>>>(mp, tp, theta_pad, wimg);
   const int grid = std::min(num_sms, C * S);
   const int actk = tp.act == ACT_RELU ? ACT_RELU : (act_keeps_z(tp.act) ? ACT_SQPRELU : -1);
-#define TU_LAUNCH(HWV, AK)                                                                                       \
+#define TU_LAUNCH(HWV, AK, TP)                                                                                   \
   do {                                                                                                           \
-    cudaFuncSetAttribute(k_train_umma<HWV, AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);     \
-    k_train_umma<HWV, AK><<<grid, TU_THREADS, tp.smem_bytes, st>>>(mp, tp, C, S, theta_pad, wimg, X, Y, N,       \
-                                                                   partial, stat_part, scratch);                 \
+    cudaFuncSetAttribute(k_train_umma<HWV, AK, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes); \
+    k_train_umma<HWV, AK, TP><<<grid, tu_threads(TP), tp.smem_bytes, st>>>(mp, tp, C, S, theta_pad, wimg, X, Y,  \
+                                                                           N, partial, stat_part, scratch);     \
   } while (0)
-  if (HW == 64) {
-    if (actk == ACT_RELU) TU_LAUNCH(64, ACT_RELU);
-    else if (actk == ACT_SQPRELU) TU_LAUNCH(64, ACT_SQPRELU);
-    else TU_LAUNCH(64, -1);
+  if (HW == 64 && tp.TPR == 4) {
+    if (actk == ACT_RELU) TU_LAUNCH(64, ACT_RELU, 4);
+    else if (actk == ACT_SQPRELU) TU_LAUNCH(64, ACT_SQPRELU, 4);
+    else TU_LAUNCH(64, -1, 4);
+  } else if (HW == 64) {
+    if (actk == ACT_RELU) TU_LAUNCH(64, ACT_RELU, 2);
+    else if (actk == ACT_SQPRELU) TU_LAUNCH(64, ACT_SQPRELU, 2);
+    else TU_LAUNCH(64, -1, 2);
   } else {
-    if (actk == ACT_RELU) TU_LAUNCH(128, ACT_RELU);
-    else if (actk == ACT_SQPRELU) TU_LAUNCH(128, ACT_SQPRELU);
-    else TU_LAUNCH(128, -1);
+    if (actk == ACT_RELU) TU_LAUNCH(128, ACT_RELU, 2);
+    else if (actk == ACT_SQPRELU) TU_LAUNCH(128, ACT_SQPRELU, 2);
+    else TU_LAUNCH(128, -1, 2);
   }
 #undef TU_LAUNCH
 }

@@ -115,6 +115,8 @@ struct TrainUmmaPlan {
   int K0p, nK0;                 // padded input width (multiple of 8) and its 32-deep chunks
   int N0w;                      // N of the block-0 weight-gradient GEMM: pad16(D + 1)
   int act;                      // activation shared by the hidden blocks
+  int TPR;                      // threads per training row in the row-worker warps (2, or 4 for 64-wide networks)
+  int fx_stride;                // floats per (thread, row) of the last-block exchange buffer: 1, 2 or 4 (>= OUT)
   int wimg_chain;               // bytes of one chain's weight operand images
   int fimg[MAXB], bimg[MAXB];   // byte offsets of the forward / backward operand image of block l
   int a_stage, b_stage;         // bytes of one ring stage

@@ -68,6 +68,26 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// The same with the two descriptors passed as 32-bit words (packed to 64 bits inside the asm block).  With 64-bit
+// descriptor arithmetic in C++ the compiler keeps the descriptors in vector registers and wraps every MMA in an
+// ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY waterfall -- 91 cycles per MMA for ANY N <= 128 (tools/umma_rate.cu), i.e. the
+// issuing thread, not the tensor pipe, sets the rate of small-N MMAs.  32-bit words derived from kernel parameters
+// and loop counters stay on the uniform datapath (UIADD3 / UMOV feeding UTCHMMA directly).
+//   lo word: (address >> 4) & 0x3FFF | (LBO >> 4) << 16        hi word: (SBO >> 4) & 0x3FFF | 1 << 14 (version)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr_bytes, uint32_t lbo_bytes) {
+  return ((saddr_bytes >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ void mma_tf32_ss32(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                              uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem]   (A: lane = row, 32-bit column = k)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
                                             bool accumulate) {
