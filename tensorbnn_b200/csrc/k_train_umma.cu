@@ -34,6 +34,9 @@
 #include "umma.cuh"
 
 namespace tbnn {
+#ifndef TU_ROLL_ALL
+#define TU_ROLL_ALL false
+#endif
 
 // TPR threads share a training row (each owns HW / TPR columns): 4 TPR row-worker warps, then the MMA issuer warp
 // (+ TMEM alloc) and the TMA producer warp.  TPR = 2: 320 threads, 168 registers.  TPR = 4 (64-wide networks): 576
@@ -227,13 +230,16 @@ __device__ int g_tu_prof_n[2];
 #endif
 
 struct TuBars {
-  uint64_t fullA[TU_NS_MAX], emptyA[TU_NS_MAX], fullB[TU_NS_MAX], emptyB[TU_NS_MAX], accfull[4], accfree[4];   // acc*: [tile slot][F/B, W]
+  uint64_t fullA[TU_NS_MAX], emptyA[TU_NS_MAX], fullB[TU_NS_MAX], emptyB[TU_NS_MAX], accfull[8], accfree[8];   // acc*: [tile slot][F/B, W]
 };
 
 // Tiles in flight per CTA.  A tile is a serial chain (F_0 -> epilogue -> F_1 -> ... -> B_1 -> epilogue -> W_0); with two
 // tiles in flight the row workers run one tile's epilogue while the tensor core runs the other tile's GEMM.  Tensor
 // memory holds two tiles' accumulators only for the 64-wide network.
-template <int HW> struct TuTiles { static constexpr int value = HW == 64 ? 2 : 1; };
+#ifndef TU_NT64
+#define TU_NT64 3
+#endif
+template <int HW> struct TuTiles { static constexpr int value = HW == 64 ? TU_NT64 : 1; };
 
 // TPR = 2: 168 registers per thread (register allocation rounds the 10 warps up to 12; a launch with 200 is refused);
 // TPR = 4: 112
@@ -276,7 +282,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
       mbar_init(&bars->fullB[i], TPR);          // a weight-gradient chunk is written by the TPR warps of one lane quarter
       mbar_init(&bars->emptyB[i], 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&bars->accfull[i], 1);
       mbar_init(&bars->accfree[i], 4 * TPR);
     }
@@ -287,12 +293,16 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tbase = tmem_slot;
-  // Tensor-memory columns of tile slot ti.  F / B accumulator (F GEMMs: the hi*hi products), the small products of the
-  // F GEMMs -- two short accumulation chains instead of one long one, the accumulator rounds toward zero -- and the W
-  // GEMMs.  HW = 128: [0,128) [128,256) [256,400); HW = 64, two slots: [128 ti, +64) [128 ti + 64, +64) [256 + 80 ti, +80).
-  auto col_big = [](int ti) -> uint32_t { return (uint32_t)(128 * ti); };
-  auto col_small = [](int ti) -> uint32_t { return (uint32_t)(NT == 2 ? 128 * ti + 64 : 128); };
-  auto col_w = [](int ti) -> uint32_t { return (uint32_t)(256 + (NT == 2 ? 80 * ti : 0)); };
+  // Tensor-memory columns of tile slot ti.  F / B accumulator "big" (F GEMMs: the hi*hi products), the small products of
+  // the F GEMMs "small" -- two short accumulation chains instead of one long one, the accumulator rounds toward zero --
+  // and the accumulator of the W GEMMs.
+  // 64-wide network, NT tile slots of 144 columns: [small / W: 80][big: 64] -- the small-product accumulator is only
+  // live during the forward pass of a tile and the weight-gradient accumulator only during its backward pass, so they
+  // share columns (the hand-over is ordered by the row workers: W operands exist only after F_{G-1} was read, and the next
+  // tile's first operand only after W_0 was drained).  128-wide network: [big 128][small 128][W 144].
+  auto col_big = [](int ti) -> uint32_t { return (uint32_t)(NT > 1 ? 144 * ti + 80 : 0); };
+  auto col_small = [](int ti) -> uint32_t { return (uint32_t)(NT > 1 ? 144 * ti : 128); };
+  auto col_w = [](int ti) -> uint32_t { return (uint32_t)(NT > 1 ? 144 * ti : 256); };
   // Segments of a tile, in order (k = 0 .. 2G): 0: X -> F_0 operands | 1..G-1: epilogue of F_{k-1} -> F_k operands |
   // G: epilogue of F_{G-1}, last block, likelihood, dZ_{G-1} -> B_{G-1}, W_{G-1} operands | G+j: epilogue of B_{G-j} ->
   // B_{G-1-j}, W_{G-1-j} operands | 2G: drain W_0.  The tiles in flight alternate segment by segment; every role walks
@@ -387,7 +397,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           umma::commit(&bars->emptyA[st]);
           umma::commit(&bars->emptyB[st]);
         };
-        if (HW == 128) {
+        if (TU_ROLL_ALL || HW == 128) {
 #pragma unroll 1
           for (int ch = 0; ch < nch; ++ch, ++cc) chunk(ch);
         } else {
@@ -405,7 +415,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           for (int k = 0; k < 2 * G; ++k) {
             for (int ti = 0; ti < ntl; ++ti) {
               prof_k = k;
-              if (HW == 128) {
+              if (TU_ROLL_ALL || HW == 128) {
                 // One call site per accumulator and a rolled chunk loop: the 128-wide kernel is held back by instruction
                 // fetch (210 KB of SASS per variant, instruction-cache hit rate 81 %): 11.87 -> 11.40 ms at C4.  The
                 // 64-wide kernel is bound by how fast this one thread issues: there the unrolled form below is 8 % faster
@@ -879,6 +889,7 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   tp.K0p = tu_pad(mp.D, 8);
   tp.nK0 = (tp.K0p + 31) / 32;
   tp.N0w = tu_pad(mp.D + 1, 16);
+  if (HW == 64 && tp.N0w > 80) return false;              // the weight-gradient accumulator of a tile slot is 80 columns
   const int chunk = 2 * tu_half(HW);
   int cur = 0;
   for (int l = 0; l < G; ++l) { tp.fimg[l] = cur; cur += (l == 0 ? tp.nK0 : HW / 32) * chunk; }
@@ -907,8 +918,9 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   const int want = env ? atoi(env) : 0;
   const int rest = tu_pad((int)sizeof(TuBars), 16) + 16;
   tp.TPR = 2;
-  if (HW == 64 && want != 2 && (size_t)(off + (pf + 2 * 4 * 128 * tp.fx_stride) * 4 + rest) <= smem_limit) tp.TPR = 4;
-  pf += 2 * tp.TPR * 128 * tp.fx_stride;                 // [tile slot][column group][row][fx_stride]
+  const int nslot = HW == 64 ? TU_NT64 : 1;
+  if (HW == 64 && want != 2 && (size_t)(off + (pf + nslot * 4 * 128 * tp.fx_stride) * 4 + rest) <= smem_limit) tp.TPR = 4;
+  pf += nslot * tp.TPR * 128 * tp.fx_stride;             // [tile slot][column group][row][fx_stride]
   off += pf * 4;
   off = tu_pad(off, 16);
   tp.off_bar = off; off += (int)sizeof(TuBars);
@@ -935,7 +947,7 @@ extern "C" int tbnn_tu_profile(long long* out, int cap) {
 #endif
 
 size_t train_umma_wimg_bytes(const TrainUmmaPlan& tp, int C) { return (size_t)C * tp.wimg_chain; }
-size_t train_umma_scratch_bytes(const TrainUmmaPlan& tp, int num_sms) { return (size_t)num_sms * 2 * tp.scratch_cta * 4; }   // two tile slots
+size_t train_umma_scratch_bytes(const TrainUmmaPlan& tp, int num_sms) { return (size_t)num_sms * 4 * tp.scratch_cta * 4; }   // up to four tile slots
 
 void launch_train_umma(const ModelPlan& mp, const TrainUmmaPlan& tp, int num_sms, int C, int S, const float* theta_pad,
                        unsigned char* wimg, float* scratch, const float* X, const float* Y, long long N,

@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(128, 1) k_rate(long long* out, int N, int mode
     const uint32_t a0 = smem_u32(smraw), b0 = a0 + 128 * 1024;
     const uint32_t id = umma::idesc_tf32(128, N, false, false);
     const uint32_t KC = 8 * ksteps;                       // K extent of the staged A tile
-    const uint32_t a_lbo = mode == 1 ? 128u : 128u * 16u, a_sbo = mode == 1 ? 32u * KC : 128u;
-    const uint32_t a_step = mode == 1 ? 256u : 2u * 128u * 16u;
+    const uint32_t a_lbo = mode != 0 ? 128u : 128u * 16u, a_sbo = mode != 0 ? 32u * KC : 128u;
+    const uint32_t a_step = mode != 0 ? 256u : 2u * 128u * 16u;
     const uint32_t bcg = 128u * (N / 8);
     // descriptors are built once; the loop only bumps the 14-bit start-address field (bytes >> 4)
     const uint64_t dA0 = umma::smem_desc(a0, a_lbo, a_sbo);
@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(128, 1) k_rate(long long* out, int N, int mode
         const uint64_t dB = dB0 + (uint64_t)(((ks & 3) * 2 * bcg) >> 4);
         const uint32_t d = tbase + (uint32_t)((ks & am) * N);     // rotate over nacc independent accumulators
         if (mode == 2) umma::mma_tf32_ts(d, tbase + 384 + 8 * (ks & 15), dB, id, true);
+        else if (mode == 3)                                 // descriptors as 32-bit words: they stay in uniform registers
+          umma::mma_tf32_ss32(d, umma::desc_lo(a0, a_lbo) + ((ks * a_step) >> 4), umma::desc_hi(a_sbo),
+                              umma::desc_lo(b0, bcg) + (((ks & 3) * 2 * bcg) >> 4), umma::desc_hi(128u), id, true);
         else umma::mma_tf32_ss(d, dA, dB, id, true);
       }
     }
@@ -61,7 +64,7 @@ int main() {
   cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int Ns[] = {16, 32, 64, 128, 256};
   for (int nacc : {1, 2, 4, 8})
-    for (int mode = 1; mode < 3; ++mode)
+    for (int mode = 1; mode < 4; ++mode)
       for (int N : Ns) {
         const int grid = 148;
         if (nacc * N > 384) continue;
@@ -73,7 +76,7 @@ int main() {
         cudaMemcpy(h.data(), d, grid * 8, cudaMemcpyDeviceToHost);
         long long mx = 0; for (auto v : h) mx = v > mx ? v : mx;
         printf("nacc %d mode %d (%s) N=%3d : %.1f cycles / MMA (128 x %d x 8)\n", nacc, mode,
-               mode == 0 ? "SS A row-groups contiguous" : mode == 1 ? "SS A col-groups contiguous" : "TS A in TMEM", N,
+               mode == 0 ? "SS A row-groups contiguous" : mode == 1 ? "SS A col-groups contiguous" : mode == 2 ? "TS A in TMEM" : "SS, 32-bit descriptor words", N,
                (double)mx / (reps * ksteps), N);
       }
   return 0;
