@@ -439,11 +439,21 @@ static int after_data(tbnn_handle* h, long long n_rows, cudaStream_t st = 0) {
       const long long nt128 = (n_rows + 127) / 128;
       double best = 1e300;
       int bestS = 1;
-      for (long long S = 1; S <= std::min<long long>(nt128, h->num_sms); ++S) {
-        const long long waves = ((long long)h->C * S + h->num_sms - 1) / h->num_sms;
-        const double cost = (double)waves * ((double)((nt128 + S - 1) / S) + 0.25);
-        if (cost < best * (1.0 - 1e-9)) { best = cost; bestS = (int)S; }
+      // A CTA keeps NT tiles in flight: a trailing group of fewer tiles costs almost as much as a full one (the tiles of
+      // a group overlap each other's GEMMs and epilogues), so item lengths are counted in groups.  The 64-wide kernel
+      // exists with 3 and with 2 tiles in flight (3 is 2 % faster per tile); the split decides which one fits.
+      const int nt_hi = h->use_tu ? train_umma_tiles_in_flight(h->tu) : 1, nt_lo = nt_hi == 3 ? 2 : nt_hi;
+      int bestNT = nt_hi;
+      for (int NT = nt_hi; NT >= nt_lo; --NT) {
+        for (long long S = 1; S <= std::min<long long>(nt128, h->num_sms); ++S) {
+          const long long waves = ((long long)h->C * S + h->num_sms - 1) / h->num_sms;
+          const long long tiles = (nt128 + S - 1) / S, rem = tiles % NT;
+          const double len = (double)(tiles - rem) + (rem ? std::max((double)rem, 0.7 * NT) : 0.0);
+          const double cost = (double)waves * (len + 0.25) * (NT == 2 && nt_hi == 3 ? 1.02 : 1.0);
+          if (cost < best * (1.0 - 1e-9)) { best = cost; bestS = (int)S; bestNT = NT; }
+        }
       }
+      if (h->use_tu) h->tu.NT = bestNT;
       h->S_tu = bestS;
     }
     if (h->use_tu) h->S = h->S_tu;   // one partial count for the sweep, the forward-only statistic sweep and finalize

@@ -236,14 +236,11 @@ struct TuBars {
 // Tiles in flight per CTA.  A tile is a serial chain (F_0 -> epilogue -> F_1 -> ... -> B_1 -> epilogue -> W_0); with two
 // tiles in flight the row workers run one tile's epilogue while the tensor core runs the other tile's GEMM.  Tensor
 // memory holds two tiles' accumulators only for the 64-wide network.
-#ifndef TU_NT64
-#define TU_NT64 3
-#endif
-template <int HW> struct TuTiles { static constexpr int value = HW == 64 ? TU_NT64 : 1; };
+constexpr int TU_NT64 = 3;                     // most tile slots of the 64-wide network (tensor memory: 3 x 144 columns)
 
 // TPR = 2: 168 registers per thread (register allocation rounds the 10 warps up to 12; a launch with 200 is refused);
 // TPR = 4: 112
-template <int HW, int ACTK, int TPR>
+template <int HW, int ACTK, int TPR, int NT>
 __global__ void __launch_bounds__(tu_threads(TPR), 1)
 k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ TrainUmmaPlan tp, int C, int S,
              const float* __restrict__ theta_pad, const unsigned char* __restrict__ wimg,
@@ -251,7 +248,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
              double* __restrict__ stat_part, float* __restrict__ scratch) {
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ uint32_t tmem_slot;
-  constexpr int NT = TuTiles<HW>::value;        // tiles in flight
+  static_assert(NT >= 1 && NT <= (HW == 64 ? TU_NT64 : 1), "tiles in flight");
   constexpr int TU_NS = tu_ns(HW);              // ring stages
   constexpr int nH = HW / 32;                   // chunks of a hidden-width contraction
   constexpr int RWT = 128 * TPR;                // row-worker threads
@@ -926,6 +923,7 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   tp.off_bar = off; off += (int)sizeof(TuBars);
   tp.smem_bytes = off;
   tp.scratch_cta = (G - 1) * HW * 128;                   // per tile slot
+  tp.NT = HW == 64 ? TU_NT64 : 1;                        // the caller may lower it to 2 (work-item planner, api.cu)
   return (size_t)off <= smem_limit;
 }
 
@@ -946,6 +944,7 @@ extern "C" int tbnn_tu_profile(long long* out, int cap) {
 }
 #endif
 
+int train_umma_tiles_in_flight(const TrainUmmaPlan& tp) { return tp.HW == 64 ? TU_NT64 : 1; }   // the most; tp.NT may be lower
 size_t train_umma_wimg_bytes(const TrainUmmaPlan& tp, int C) { return (size_t)C * tp.wimg_chain; }
 size_t train_umma_scratch_bytes(const TrainUmmaPlan& tp, int num_sms) { return (size_t)num_sms * 4 * tp.scratch_cta * 4; }   // up to four tile slots
 
@@ -957,25 +956,28 @@ void launch_train_umma(const ModelPlan& mp, const TrainUmmaPlan& tp, int num_sms
   k_train_prep<<<dim3((groups + 255) / 256, C), 256, 0, st>>>(mp, tp, theta_pad, wimg);
   const int grid = std::min(num_sms, C * S);
   const int actk = tp.act == ACT_RELU ? ACT_RELU : (act_keeps_z(tp.act) ? ACT_SQPRELU : -1);
-#define TU_LAUNCH(HWV, AK, TP)                                                                                   \
+#define TU_LAUNCH(HWV, AK, TP, NTV)                                                                              \
   do {                                                                                                           \
-    cudaFuncSetAttribute(k_train_umma<HWV, AK, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes); \
-    k_train_umma<HWV, AK, TP><<<grid, tu_threads(TP), tp.smem_bytes, st>>>(mp, tp, C, S, theta_pad, wimg, X, Y,  \
-                                                                           N, partial, stat_part, scratch);     \
+    cudaFuncSetAttribute(k_train_umma<HWV, AK, TP, NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                         tp.smem_bytes);                                                                         \
+    k_train_umma<HWV, AK, TP, NTV><<<grid, tu_threads(TP), tp.smem_bytes, st>>>(                                 \
+        mp, tp, C, S, theta_pad, wimg, X, Y, N, partial, stat_part, scratch);                                    \
   } while (0)
-  if (HW == 64 && tp.TPR == 4) {
-    if (actk == ACT_RELU) TU_LAUNCH(64, ACT_RELU, 4);
-    else if (actk == ACT_SQPRELU) TU_LAUNCH(64, ACT_SQPRELU, 4);
-    else TU_LAUNCH(64, -1, 4);
-  } else if (HW == 64) {
-    if (actk == ACT_RELU) TU_LAUNCH(64, ACT_RELU, 2);
-    else if (actk == ACT_SQPRELU) TU_LAUNCH(64, ACT_SQPRELU, 2);
-    else TU_LAUNCH(64, -1, 2);
+#define TU_LAUNCH_ACT(HWV, TP, NTV)                                                                              \
+  do {                                                                                                           \
+    if (actk == ACT_RELU) TU_LAUNCH(HWV, ACT_RELU, TP, NTV);                                                     \
+    else if (actk == ACT_SQPRELU) TU_LAUNCH(HWV, ACT_SQPRELU, TP, NTV);                                          \
+    else TU_LAUNCH(HWV, -1, TP, NTV);                                                                            \
+  } while (0)
+  if (HW == 64) {
+    if (tp.TPR == 4 && tp.NT == 3) TU_LAUNCH_ACT(64, 4, 3);
+    else if (tp.TPR == 4) TU_LAUNCH_ACT(64, 4, 2);
+    else if (tp.NT == 3) TU_LAUNCH_ACT(64, 2, 3);
+    else TU_LAUNCH_ACT(64, 2, 2);
   } else {
-    if (actk == ACT_RELU) TU_LAUNCH(128, ACT_RELU, 2);
-    else if (actk == ACT_SQPRELU) TU_LAUNCH(128, ACT_SQPRELU, 2);
-    else TU_LAUNCH(128, -1, 2);
+    TU_LAUNCH_ACT(128, 2, 1);
   }
+#undef TU_LAUNCH_ACT
 #undef TU_LAUNCH
 }
 

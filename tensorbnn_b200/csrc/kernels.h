@@ -115,6 +115,7 @@ struct TrainUmmaPlan {
   int K0p, nK0;                 // padded input width (multiple of 8) and its 32-deep chunks
   int N0w;                      // N of the block-0 weight-gradient GEMM: pad16(D + 1)
   int act;                      // activation shared by the hidden blocks
+  int NT;                       // tiles a CTA keeps in flight: 1 (128-wide), 2 or 3 (64-wide; chosen with the work-item split)
   int TPR;                      // threads per training row in the row-worker warps (2, or 4 for 64-wide networks)
   int fx_stride;                // floats per (thread, row) of the last-block exchange buffer: 1, 2 or 4 (>= OUT)
   int wimg_chain;               // bytes of one chain's weight operand images
@@ -127,6 +128,7 @@ struct TrainUmmaPlan {
 };
 bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit);
 size_t train_umma_wimg_bytes(const TrainUmmaPlan& tp, int C);
+int train_umma_tiles_in_flight(const TrainUmmaPlan& tp);   // most tiles a CTA can keep in flight (tp.NT = the number in use)
 size_t train_umma_scratch_bytes(const TrainUmmaPlan& tp, int num_sms);
 void launch_train_umma(const ModelPlan& mp, const TrainUmmaPlan& tp, int num_sms, int C, int S, const float* theta_pad,
                        unsigned char* wimg, float* scratch, const float* X, const float* Y, long long N,

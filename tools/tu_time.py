@@ -6,7 +6,9 @@ from tensorbnn_b200 import workloads as wl
 from tensorbnn_b200.engine import Engine
 which = sys.argv[1]
 flags_list = [int(f) for f in sys.argv[2:]] or [0, 64]
-if which == "c3":
+if which.startswith("c3:"):                      # c3:<chains>, e.g. c3:128 = one GPU's share of the 8-GPU split
+    cfg = wl.c3(chains=int(which[3:]))
+elif which == "c3":
     cfg = wl.c3(chains=1024)
 elif which == "c3s":
     cfg = wl.c3(chains=148)
