@@ -63,7 +63,9 @@ k_predict_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Pre
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bars[2];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: the compiler then treats everything derived from it (roles, column groups, tensor-
+  // memory columns) as warp-uniform -- uniform branches and registers instead of per-thread ones
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int wg = warp >> 2, wq = warp & 3, trow = 32 * wq + lane;
   float* acc = reinterpret_cast<float*>(smraw + pu.acc_ofs);
   const long long r_begin = (long long)blockIdx.x * rows_per_cta;
@@ -210,14 +212,16 @@ k_predict_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Pre
           const uint32_t bh = smem_u32(smraw + pu.wofs[l]), blo = bh + (uint32_t)pu.wbytes[l];
           const uint32_t cg = 128u * (uint32_t)(Np >> 3);
           const uint32_t d = umma::tmem_addr(tbase, 0, colZ);
+          // B descriptors as 32-bit words: they stay in uniform registers and advance with one add per k step (with
+          // 64-bit descriptors every MMA was wrapped in an R2UR waterfall: 91 cycles per MMA, profiles/r2h_summary.md)
+          const uint32_t hiw = umma::desc_hi(128u), stepB = (2u * cg) >> 4;
+          const uint32_t bH0 = umma::desc_lo(bh, cg), bL0 = umma::desc_lo(blo, cg);
           for (int ks = 0; ks < (Kp >> 3); ++ks) {
-            const uint64_t dBh = umma::smem_desc(bh + ks * 2 * cg, cg, 128u);
-            const uint64_t dBl = umma::smem_desc(blo + ks * 2 * cg, cg, 128u);
             const uint32_t tAh = umma::tmem_addr(tbase, 0, colAh + 8 * ks);
             const uint32_t tAl = umma::tmem_addr(tbase, 0, colAl + 8 * ks);
-            umma::mma_tf32_ts(d, tAl, dBh, id, ks > 0);
-            umma::mma_tf32_ts(d, tAh, dBl, id, true);
-            umma::mma_tf32_ts(d, tAh, dBh, id, true);
+            umma::mma_tf32_ts32(d, tAl, bH0 + ks * stepB, hiw, id, ks > 0);
+            umma::mma_tf32_ts32(d, tAh, bL0 + ks * stepB, hiw, id, true);
+            umma::mma_tf32_ts32(d, tAh, bH0 + ks * stepB, hiw, id, true);
           }
           umma::commit(&bars[wg]);
         }
