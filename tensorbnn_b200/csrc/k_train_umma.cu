@@ -910,23 +910,30 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   tp.par_sraw = pf; pf += G * HW;
   tp.par_wl = pf; pf += mp.OUT * HW + 4;
   tp.par_accl = pf; pf += 4 * (mp.OUT * HW + 4) + 16;    // one per lane quarter, + 8 doubles of reduction scratch
-  // Four threads per row for the 64-wide network when the exchange buffer of the last block still fits; TBNN_TU_TPR=2
-  // in the environment keeps two (A/B measurements).
+  // 64-wide network: four threads per row and three tile slots when the exchange buffer of the last block
+  // ([tile slot][thread of the row][row][fx_stride] floats) still fits, else fewer; TBNN_TU_TPR=2 in the environment keeps
+  // two threads per row (A/B measurements, tests).
   tp.fx_stride = mp.OUT == 1 ? 1 : (mp.OUT == 2 ? 2 : 4);
   tp.par_fx = pf;
   const char* env = getenv("TBNN_TU_TPR");
   const int want = env ? atoi(env) : 0;
   const int rest = tu_pad((int)sizeof(TuBars), 16) + 16;
   tp.TPR = 2;
-  const int nslot = HW == 64 ? TU_NT64 : 1;
-  if (HW == 64 && want != 2 && (size_t)(off + (pf + nslot * 4 * 128 * tp.fx_stride) * 4 + rest) <= smem_limit) tp.TPR = 4;
-  pf += nslot * tp.TPR * 128 * tp.fx_stride;             // [tile slot][column group][row][fx_stride]
+  tp.NTmax = HW == 64 ? 2 : 1;
+  if (HW == 64) {
+    const int cand[4][2] = {{4, 3}, {4, 2}, {2, 3}, {2, 2}};
+    for (auto& c : cand) {
+      if (want == 2 && c[0] != 2) continue;
+      if ((size_t)(off + (pf + c[1] * c[0] * 128 * tp.fx_stride) * 4 + rest) <= smem_limit) { tp.TPR = c[0]; tp.NTmax = c[1]; break; }
+    }
+  }
+  pf += tp.NTmax * tp.TPR * 128 * tp.fx_stride;
   off += pf * 4;
   off = tu_pad(off, 16);
   tp.off_bar = off; off += (int)sizeof(TuBars);
   tp.smem_bytes = off;
   tp.scratch_cta = (G - 1) * HW * 128;                   // per tile slot
-  tp.NT = HW == 64 ? TU_NT64 : 1;                        // the caller may lower it to 2 (work-item planner, api.cu)
+  tp.NT = tp.NTmax;                                      // the caller may lower it to 2 (work-item planner, api.cu)
   return (size_t)off <= smem_limit;
 }
 
@@ -947,7 +954,7 @@ extern "C" int tbnn_tu_profile(long long* out, int cap) {
 }
 #endif
 
-int train_umma_tiles_in_flight(const TrainUmmaPlan& tp) { return tp.HW == 64 ? TU_NT64 : 1; }   // the most; tp.NT may be lower
+int train_umma_tiles_in_flight(const TrainUmmaPlan& tp) { return tp.NTmax; }   // the most; tp.NT may be lower
 size_t train_umma_wimg_bytes(const TrainUmmaPlan& tp, int C) { return (size_t)C * tp.wimg_chain; }
 size_t train_umma_scratch_bytes(const TrainUmmaPlan& tp, int num_sms) { return (size_t)num_sms * 4 * tp.scratch_cta * 4; }   // up to four tile slots
 

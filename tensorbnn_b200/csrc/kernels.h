@@ -115,6 +115,7 @@ struct TrainUmmaPlan {
   int K0p, nK0;                 // padded input width (multiple of 8) and its 32-deep chunks
   int N0w;                      // N of the block-0 weight-gradient GEMM: pad16(D + 1)
   int act;                      // activation shared by the hidden blocks
+  int NTmax;                    // tile slots the shared-memory plan has room for (64-wide: 3 or 2)
   int NT;                       // tiles a CTA keeps in flight: 1 (128-wide), 2 or 3 (64-wide; chosen with the work-item split)
   int TPR;                      // threads per training row in the row-worker warps (2, or 4 for 64-wide networks)
   int fx_stride;                // floats per (thread, row) of the last-block exchange buffer: 1, 2 or 4 (>= OUT)

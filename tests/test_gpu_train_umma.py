@@ -83,6 +83,49 @@ def test_train_umma_matches_oracle_and_ffma_engine(name):
         assert rel(g[c], gf[c]) <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["c3s", "relu64", "tanh64"])
+def test_train_umma_two_threads_per_row_variant(name, monkeypatch):
+    """64-wide networks run with four threads per training row by default; TBNN_TU_TPR=2 (read when the handle is
+    planned) keeps two.  Both variants must agree with the oracle and with each other."""
+    arch, lik, X, Y, TH, HY = _problem(name)
+    C = TH.shape[0]
+    eng4 = _engine(arch, lik, chains=C)
+    eng4.set_data(X, Y)
+    lp4, g4, _ = eng4.logp_grad(TH, HY)
+    monkeypatch.setenv("TBNN_TU_TPR", "2")
+    eng2 = _engine(arch, lik, chains=C)
+    eng2.set_data(X, Y)
+    assert eng2.sweep_info()["kernel"] == "k_train_umma"
+    assert eng2.sweep_info()["smem_bytes"] != eng4.sweep_info()["smem_bytes"]          # a different plan was made
+    lp2, g2, _ = eng2.logp_grad(TH, HY)
+    lp4, g4, lp2, g2 = (t.cpu().numpy() for t in (lp4, g4, lp2, g2))
+    for c in range(C):
+        lp_ref, g_ref = analytic.main_value_and_grad(arch, lik, r32(TH[c]), r32(HY[c]), r32(X), r32(Y))
+        assert abs(lp2[c] - lp_ref) <= 1e-5 * abs(lp_ref) and rel(g2[c], g_ref) <= 1e-5, (name, c, rel(g2[c], g_ref))
+        assert abs(lp2[c] - lp4[c]) <= 5e-6 * abs(lp4[c]) and rel(g2[c], g4[c]) <= 1e-5
+
+
+def test_train_umma_64_wide_three_outputs():
+    """Three outputs on a 64-wide network: the last-block exchange buffer of the four-threads-per-row variant does not
+    fit, the planner falls back to two threads per row (fx_stride 4)."""
+    arch = wl.mlp_arch([4, 64, 64, 3], "dense", "relu")
+    lik = ("gaussian", 0.3)
+    rng = np.random.default_rng(7)
+    N, C = 300, 2
+    X, Y = rng.normal(size=(N, 4)), rng.normal(size=(N, 3))
+    P, H = wl.init_theta(arch).size, wl.init_hyper(arch, lik).size
+    TH = np.stack([wl.init_theta(arch, seed=3 + c) * 0.7 + 0.05 * rng.normal(size=P) for c in range(C)])
+    HY = np.stack([wl.init_hyper(arch, lik) + 0.05 * rng.normal(size=H) for c in range(C)])
+    eng = _engine(arch, lik, chains=C)
+    eng.set_data(X, Y)
+    assert eng.sweep_info()["kernel"] == "k_train_umma"
+    lp, g, _ = eng.logp_grad(TH, HY)
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    for c in range(C):
+        lp_ref, g_ref = analytic.main_value_and_grad(arch, lik, r32(TH[c]), r32(HY[c]), r32(X), r32(Y))
+        assert abs(lp[c] - lp_ref) <= 1e-5 * abs(lp_ref) and rel(g[c], g_ref) <= 1e-5, (c, rel(g[c], g_ref))
+
+
 def test_train_umma_trajectory_and_transition_match_oracle():
     """Fixed-momentum L-step trajectory end point within 1e-4 and the Metropolis decision, tcgen05 sweep inside."""
     from oracle import hmc
