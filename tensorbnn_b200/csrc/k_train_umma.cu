@@ -248,7 +248,10 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
              double* __restrict__ stat_part, float* __restrict__ scratch) {
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ uint32_t tmem_slot;
-  static_assert(NT >= 1 && NT <= (HW == 64 ? TU_NT64 : 1), "tiles in flight");
+  static_assert(NT >= 1 && NT <= (HW == 64 ? TU_NT64 : 2), "tiles in flight");
+  // 128-wide network with two tiles in flight: tensor memory is 2 x (128 + 128) columns, so the weight-gradient GEMMs
+  // have no room for the constant-one column -- the bias gradients are column sums on the CUDA cores instead
+  constexpr bool BIASCS = HW == 128 && NT == 2;
   constexpr int TU_NS = tu_ns(HW);              // ring stages
   constexpr int nH = HW / 32;                   // chunks of a hidden-width contraction
   constexpr int RWT = 128 * TPR;                // row-worker threads
@@ -256,7 +259,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
   constexpr int HH = HW / TPR;                  // columns per row worker (TPR threads share a row)
   constexpr int nP = HH / 16;                   // 16-column pieces per row worker
   static_assert(HH == 16 || HH == 32 || HH == 64, "columns per row worker");
-  constexpr int NWH = HW + 16;                  // N of a hidden weight-gradient GEMM: [A | 1 | pad]
+  constexpr int NWH = BIASCS ? HW : HW + 16;    // N of a hidden weight-gradient GEMM: [A | 1 | pad] (BIASCS: [A])
   constexpr bool SLOPES = ACTK == ACT_SQPRELU;
   constexpr bool STACKQ = SLOPES && HW == 64;   // slope gradients ride in operand rows 64..127
   // warp index through a shuffle: the compiler then treats everything derived from it (roles, column groups, tensor-
@@ -300,9 +303,10 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
   // live during the forward pass of a tile and the weight-gradient accumulator only during its backward pass, so they
   // share columns (the hand-over is ordered by the row workers: W operands exist only after F_{G-1} was read, and the next
   // tile's first operand only after W_0 was drained).  128-wide network: [big 128][small 128][W 144].
-  auto col_big = [](int ti) -> uint32_t { return (uint32_t)(NT > 1 ? 144 * ti + 80 : 0); };
-  auto col_small = [](int ti) -> uint32_t { return (uint32_t)(NT > 1 ? 144 * ti : 128); };
-  auto col_w = [](int ti) -> uint32_t { return (uint32_t)(NT > 1 ? 144 * ti : 256); };
+  constexpr int SLOTW = HW == 64 ? 144 : 256, SMALLW = HW == 64 ? 80 : 128;   // columns of a tile slot / of its shared part
+  auto col_big = [](int ti) -> uint32_t { return (uint32_t)(NT > 1 ? SLOTW * ti + SMALLW : 0); };
+  auto col_small = [](int ti) -> uint32_t { return (uint32_t)(NT > 1 ? SLOTW * ti : 128); };
+  auto col_w = [](int ti) -> uint32_t { return (uint32_t)(NT > 1 ? SLOTW * ti : 256); };
   // Segments of a tile, in order (k = 0 .. 2G): 0: X -> F_0 operands | 1..G-1: epilogue of F_{k-1} -> F_k operands |
   // G: epilogue of F_{G-1}, last block, likelihood, dZ_{G-1} -> B_{G-1}, W_{G-1} operands | G+j: epilogue of B_{G-j} ->
   // B_{G-1-j}, W_{G-1-j} operands | 2G: drain W_0.  The tiles in flight alternate segment by segment; every role walks
@@ -450,6 +454,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
     float* wl_s = par + tp.par_wl;                       // [OUT][HW], then bias [4]
     float* accl_s = par + tp.par_accl + wq * (OUT * HW + 4);   // per warp quarter [OUT][HW] + [4]: gradient of the last
                                                          // block (summed in fixed order at the end: reruns are bit-identical)
+    float* accb_s = par + tp.par_accb + wq * (G * HW);   // BIASCS: per lane quarter [G][HW] bias-gradient column sums
     const BlockPlan& bL = mp.b[G];
     double stat = 0.0;
     float* gout = nullptr;
@@ -512,7 +517,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           for (int i = 0; i < 16; i += 4) red_add4(gw + n0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
-      if (grp == TPR - 1) {
+      if (!BIASCS && grp == TPR - 1) {
         float v[8];
         umma::tmem_ld8(tbase + lane_t + col_w(ti) + HW, v);
         umma::tmem_ld_wait();
@@ -555,7 +560,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
               for (int i = 0; i < 4; ++i)
                 put_t_at(tbb, tbb + half, 4 * g4 + i, tu_from_keep<ACTK>(hact, k4[i], SLOPES ? sl[4 * g4 + i] : 0.f));
             }
-            if (grp == TPR - 1) put_t(sb, half, cgs, HW, lane, 1.f);
+            if (!BIASCS && grp == TPR - 1) put_t(sb, half, cgs, HW, lane, 1.f);
           } else if (grp == 0) {
             const int cgs = tu_cgs(tp.N0w), half = tu_half(tp.N0w);
             for (int k = 0; k < D; ++k) put_t(sb, half, cgs, k, lane, valid ? xrow[k] : 0.f);
@@ -568,6 +573,16 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
         done(st, false);                                   // the owner fenced above
       }
       cc += 4;
+      if (BIASCS && l >= 1) {                              // bias gradient of block l: column sums of dZ_l over this warp's rows
+#pragma unroll
+        for (int g = 0; g < (HH >= 32 ? HH / 32 : 1); ++g) {
+          float pr[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pr[i] = dz[(HH >= 32 ? 32 * g : 0) + i];
+          const float cs = colsum32(pr, lane);
+          accb_s[l * HW + cb + 32 * g + lane] += cs;
+        }
+      }
     };
 
     for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
@@ -595,6 +610,8 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
 #pragma unroll
         for (int w = 0; w < 4; ++w) par[tp.par_accl + w * (OUT * HW + 4) + e] = 0.f;
       }
+      if (BIASCS)
+        for (int e = tid; e < 4 * G * HW; e += RWT) par[tp.par_accb + e] = 0.f;
       for (int i = 4 * tid; i < mp.Ppad; i += 4 * RWT) *reinterpret_cast<float4*>(gout + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       __threadfence();
       ew_barrier<RWT>();
@@ -852,6 +869,14 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
           const int e = OUT * HW + tid;
           gout[bL.pb + tid] = ((a0[e] + a0[ws + e]) + a0[2 * ws + e]) + a0[3 * ws + e];
         }
+        if (BIASCS) {                                      // bias gradients of blocks 1 .. G-1 (fixed order over the lane quarters)
+          const float* b0s = par + tp.par_accb;
+          const int wsb = G * HW;
+          for (int e = HW + tid; e < G * HW; e += RWT) {
+            const int l = e / HW, j = e - l * HW;
+            gout[mp.b[l].pb + j] = ((b0s[e] + b0s[wsb + e]) + b0s[2 * wsb + e]) + b0s[3 * wsb + e];
+          }
+        }
       }
       {
         double* red = reinterpret_cast<double*>(par + tp.par_accl + 4 * (OUT * HW + 4));
@@ -910,6 +935,7 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
   tp.par_sraw = pf; pf += G * HW;
   tp.par_wl = pf; pf += mp.OUT * HW + 4;
   tp.par_accl = pf; pf += 4 * (mp.OUT * HW + 4) + 16;    // one per lane quarter, + 8 doubles of reduction scratch
+  tp.par_accb = pf; pf += HW == 128 ? 4 * G * HW : 0;    // 128-wide, two tiles in flight: bias-gradient column sums per lane quarter
   // 64-wide network: four threads per row and three tile slots when the exchange buffer of the last block
   // ([tile slot][thread of the row][row][fx_stride] floats) still fits, else fewer; TBNN_TU_TPR=2 in the environment keeps
   // two threads per row (A/B measurements, tests).
@@ -926,6 +952,11 @@ bool plan_train_umma(const ModelPlan& mp, TrainUmmaPlan& tp, size_t smem_limit) 
       if (want == 2 && c[0] != 2) continue;
       if ((size_t)(off + (pf + c[1] * c[0] * 128 * tp.fx_stride) * 4 + rest) <= smem_limit) { tp.TPR = c[0]; tp.NTmax = c[1]; break; }
     }
+  }
+  if (HW == 128) {                                       // two tiles in flight when the second exchange buffer fits
+    const char* e128 = getenv("TBNN_TU_NT128");          // TBNN_TU_NT128=1: one tile in flight (A/B measurements, tests)
+    const int want128 = e128 ? atoi(e128) : 0;
+    if (want128 != 1 && tp.N0w <= 128 && (size_t)(off + (pf + 2 * tp.TPR * 128 * tp.fx_stride) * 4 + rest) <= smem_limit) tp.NTmax = 2;
   }
   pf += tp.NTmax * tp.TPR * 128 * tp.fx_stride;
   off += pf * 4;
@@ -985,7 +1016,8 @@ void launch_train_umma(const ModelPlan& mp, const TrainUmmaPlan& tp, int num_sms
     else if (tp.NT == 3) TU_LAUNCH_ACT(64, 2, 3);
     else TU_LAUNCH_ACT(64, 2, 2);
   } else {
-    TU_LAUNCH_ACT(128, 2, 1);
+    if (tp.NT == 2) TU_LAUNCH_ACT(128, 2, 2);
+    else TU_LAUNCH_ACT(128, 2, 1);
   }
 #undef TU_LAUNCH_ACT
 #undef TU_LAUNCH

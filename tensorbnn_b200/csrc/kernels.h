@@ -123,7 +123,7 @@ struct TrainUmmaPlan {
   int fimg[MAXB], bimg[MAXB];   // byte offsets of the forward / backward operand image of block l
   int a_stage, b_stage;         // bytes of one ring stage
   int off_a, off_b, off_par, off_bar;                          // shared-memory byte offsets
-  int par_bias, par_slope, par_sraw, par_wl, par_accl, par_fx;   // float offsets inside the parameter region
+  int par_bias, par_slope, par_sraw, par_wl, par_accl, par_accb, par_fx;   // float offsets inside the parameter region
   int smem_bytes;
   int scratch_cta;              // floats of pre-activation scratch per CTA
 };
