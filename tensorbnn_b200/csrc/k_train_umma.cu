@@ -34,6 +34,9 @@
 #include "umma.cuh"
 
 namespace tbnn {
+#ifndef TU_SHFL128
+#define TU_SHFL128 false
+#endif
 #ifndef TU_ROLL_ALL
 #define TU_ROLL_ALL false
 #endif
@@ -265,7 +268,7 @@ k_train_umma(const __grid_constant__ ModelPlan mp, const __grid_constant__ Train
   // warp index through a shuffle: the compiler then treats everything derived from it (roles, column groups, tensor-
   // memory columns) as warp-uniform -- uniform branches and registers instead of per-thread ones
   // (measured per width: C3 4.75 -> 4.30 ms; the 128-wide kernel lost 2 % with it and keeps the plain form)
-  const int tid = threadIdx.x, warp = HW == 64 ? __shfl_sync(0xffffffffu, tid >> 5, 0) : (tid >> 5), lane = tid & 31;
+  const int tid = threadIdx.x, warp = TU_SHFL128 || HW == 64 ? __shfl_sync(0xffffffffu, tid >> 5, 0) : (tid >> 5), lane = tid & 31;
   const int G = tp.G, D = mp.D, OUT = mp.OUT, hact = tp.act;
   TuBars* bars = reinterpret_cast<TuBars*>(smraw + tp.off_bar);
   float* par = reinterpret_cast<float*>(smraw + tp.off_par);
