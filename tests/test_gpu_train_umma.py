@@ -105,6 +105,29 @@ def test_train_umma_two_threads_per_row_variant(name, monkeypatch):
         assert abs(lp2[c] - lp4[c]) <= 5e-6 * abs(lp4[c]) and rel(g2[c], g4[c]) <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["c4s", "bern128"])      # (3-output networks plan one tile in flight either way)
+def test_train_umma_128_wide_one_tile_in_flight_variant(name, monkeypatch):
+    """128-wide networks run two tiles in flight by default (bias gradients as warp column sums); TBNN_TU_NT128=1
+    keeps one (bias gradients from the constant-one column of the weight-gradient GEMM).  Both must agree with the
+    oracle and with each other."""
+    arch, lik, X, Y, TH, HY = _problem(name)
+    C = TH.shape[0]
+    eng2 = _engine(arch, lik, chains=C)
+    eng2.set_data(X, Y)
+    lp2, g2, _ = eng2.logp_grad(TH, HY)
+    monkeypatch.setenv("TBNN_TU_NT128", "1")
+    eng1 = _engine(arch, lik, chains=C)
+    eng1.set_data(X, Y)
+    assert eng1.sweep_info()["kernel"] == "k_train_umma"
+    assert eng1.sweep_info()["smem_bytes"] != eng2.sweep_info()["smem_bytes"]          # a different plan was made
+    lp1, g1, _ = eng1.logp_grad(TH, HY)
+    lp1, g1, lp2, g2 = (t.cpu().numpy() for t in (lp1, g1, lp2, g2))
+    for c in range(C):
+        lp_ref, g_ref = analytic.main_value_and_grad(arch, lik, r32(TH[c]), r32(HY[c]), r32(X), r32(Y))
+        assert abs(lp1[c] - lp_ref) <= 1e-5 * abs(lp_ref) and rel(g1[c], g_ref) <= 1e-5, (name, c, rel(g1[c], g_ref))
+        assert abs(lp1[c] - lp2[c]) <= 5e-6 * abs(lp2[c]) and rel(g1[c], g2[c]) <= 1e-5
+
+
 def test_train_umma_64_wide_three_outputs():
     """Three outputs on a 64-wide network: the last-block exchange buffer of the four-threads-per-row variant does not
     fit, the planner falls back to two threads per row (fx_stride 4)."""
