@@ -11,21 +11,27 @@
 // Shapes: networks whose dense blocks 0..G-1 all have the same output width HW in {64, 128} and the same
 // activation, followed by one last block with <= 4 outputs (C3: 1-64-64-64-1 SquarePrelu, C4: 32-128-128-128-1 ReLU).
 //
-// One persistent CTA per SM, 6 warps, three roles over two 3-stage operand rings in shared memory:
-//   warps 0-3  row workers: thread = one training row of the 128-row tile.  They read accumulators from tensor
-//              memory (tcgen05.ld), apply bias / activation / derivatives, and WRITE MMA OPERANDS: K-major chunks of
-//              32 features for the forward (A_l) and data-gradient (dZ_l) GEMMs, and transposed (K = rows) chunks for
-//              the weight-gradient GEMMs -- chunk q of those holds the 32 rows of warp q.  hi/lo TF32 split, plain
+// One persistent CTA per SM, three roles over two operand rings in shared memory (4 stages for the 64-wide network, 3
+// for the 128-wide one):
+//   4 TPR row-worker warps: TPR threads share a training row of the 128-row tile (TPR = 4 for the 64-wide network, 2 for
+//              the 128-wide one), each owning HW / TPR columns.  They read accumulators from tensor memory
+//              (tcgen05.ld), apply bias / activation / derivatives, and WRITE MMA OPERANDS: K-major chunks of 32 features
+//              for the forward (A_l) and data-gradient (dZ_l) GEMMs, and transposed (K = rows) chunks for the
+//              weight-gradient GEMMs -- chunk q of those holds the 32 rows of lane quarter q.  hi/lo TF32 split, plain
 //              SWIZZLE_NONE core matrices whose column-group stride is padded by 16 bytes so the transposed 4-byte
 //              stores are bank-conflict free.
-//   warp 4     MMA issuer (one thread): per 32-deep chunk and 8-deep k step lo*hi + hi*lo + hi*hi.
-//   warp 5     TMA producer (one thread): streams pre-split, pre-tiled weight operands (k_train_prep) from L2 with
+//   1 warp     MMA issuer (one thread): per 32-deep chunk and 8-deep k step lo*hi + hi*lo + hi*hi.  Its descriptors are
+//              32-bit words on the uniform datapath (umma::mma_tf32_ss32) -- see the comment there.
+//   1 warp     TMA producer (one thread): streams pre-split, pre-tiled weight operands (k_train_prep) from L2 with
 //              cp.async.bulk; a 128-wide network does not fit its weights (2 layers x 2 orientations x hi/lo x 64 KB)
 //              in shared memory, so they are streamed per tile (~0.5 MB / tile, L2 resident).
+// Two or three tiles are in flight per CTA (64-wide: 3 or 2, 128-wide: 2), alternating segment by segment, so one
+// tile's epilogue overlaps the others' GEMMs.
 // GEMM order per tile: F_0 .. F_{G-1} | B_{G-1}, W_{G-1}, .., B_1, W_1, W_0   (F: Z_l = A_{l-1} W_l^T, B: dA_{l-1} =
 // dZ_l W_l, W: [dW_l | db_l] = dZ_l^T [A_{l-1} | 1]).  The bias gradient falls out of a constant-one operand row; with
 // HW = 64 the free upper half of the M = 128 operand carries z*dA so the slope gradients (Prelu / SquarePrelu) fall
-// out of the same column.  Weight gradients are drained per tile from tensor memory and added to this CTA's slice
+// out of the same column.  (128-wide network with two tiles in flight: tensor memory has no room for that column, the
+// bias gradients of the hidden blocks are warp column sums.)  Weight gradients are drained per tile from tensor memory and added to this CTA's slice
 // of the partial buffer with vector reductions (red.global.add.v4.f32): the accumulation chain inside the tensor
 // core stays 48 MMAs long (its accumulator rounds toward zero, profiles/r1d_summary.md).
 // Pre-activations of blocks 0..G-2 are parked in a per-CTA global scratch (L2 resident) between forward and backward.
@@ -72,16 +78,6 @@ __device__ __forceinline__ void sts32(uint32_t saddr, float v) {
 __device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// 32 accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  float a[16], b[16];
-  umma::tmem_ld16(taddr, a);
-  umma::tmem_ld16(taddr + 16, b);
-  umma::tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { v[i] = a[i]; v[16 + i] = b[i]; }
-}
-
 // 16 accumulator columns
 __device__ __forceinline__ void tmem_ld16w(uint32_t taddr, float (&v)[16]) {
   umma::tmem_ld16(taddr, v);
